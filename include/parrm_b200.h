@@ -1,0 +1,154 @@
+/*
+ * parrm_b200.h -- C ABI of libparrm_b200.so: the PARRM hot path on NVIDIA B200 (sm_100a).
+ *
+ * The reference (neuromodulation/PyPARRM) is pure Python and has no FFI of its
+ * own; its boundary for this path is the private seams of `pyparrm.PARRM`
+ * (src/pyparrm/parrm.py).  Each entry point below replaces one of those seams
+ * and cites it.  The Python host (`pyparrm_b200/parrm.py`) binds these with
+ * ctypes (`pyparrm_b200/_native.py`); INTEGRATION.md shows the same stub as a
+ * maintainer of the reference would add it.
+ *
+ * Conventions
+ *   - Every function returns a parrm_status_t (0 = success).  On failure a
+ *     thread-local message is available from parrm_last_error().
+ *   - Pointers named d_* are DEVICE pointers owned by the caller (PyTorch tensors
+ *     in the shipped host); h_* are host pointers.  The library never allocates or
+ *     frees device memory and never synchronises the device: work is enqueued on
+ *     `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *     Scratch space is passed in as (d_workspace, workspace_bytes); sizes come
+ *     from the *_workspace_bytes functions.
+ *   - Recordings are row-major [n_chans, n_samples] with a row stride `ld`
+ *     counted in elements.  dtype selects float64 (reference arithmetic,
+ *     rel. err <= 1e-9) or float32 storage (<= 1e-4).
+ *   - No global mutable state apart from the thread-local error string.
+ */
+#ifndef PARRM_B200_H
+#define PARRM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PARRM_B200_ABI_VERSION 1
+
+typedef enum {
+  PARRM_OK = 0,
+  PARRM_ERR_INVALID_ARGUMENT = 1,
+  PARRM_ERR_CUDA = 2,           /* a CUDA runtime call failed (no device, launch error, ...) */
+  PARRM_ERR_WORKSPACE = 3,      /* workspace too small */
+  PARRM_ERR_UNSUPPORTED = 4     /* e.g. bandwidth above PARRM_MAX_BANDWIDTH */
+} parrm_status_t;
+
+typedef enum { PARRM_F64 = 0, PARRM_F32 = 1 } parrm_dtype_t;
+
+/* filter_direction strings of PARRM.create_filter (parrm.py:710-714, 817-820) */
+typedef enum { PARRM_DIR_BOTH = 0, PARRM_DIR_PAST = 1, PARRM_DIR_FUTURE = 2 } parrm_direction_t;
+
+#define PARRM_MAX_BANDWIDTH 23  /* harmonics per candidate; the reference uses 5/10/20 (parrm.py:295) */
+
+int         parrm_abi_version(void);
+const char* parrm_last_error(void);
+/* Number of visible CUDA devices (0 on a CPU-only host; never fails). */
+int         parrm_device_count(void);
+/* 1 if the host pointer lies in page-locked (pinned / registered) memory, else 0.  The host
+ * pipeline uses it to choose between direct async copies and staged ones. */
+int         parrm_host_is_pinned(const void* h_ptr);
+/* cudaMemcpyAsync wrappers for the host pipeline (pageable pointers are legal but make the
+ * copy synchronous with respect to the host, as CUDA defines). */
+int         parrm_copy_h2d_async(void* d_dst, const void* h_src, size_t bytes, void* stream);
+int         parrm_copy_d2h_async(void* h_dst, const void* d_src, size_t bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Standardisation: PARRM._standardise_data (parrm.py:272-280)
+ *   d[c,t] = x[c,t+1]-x[c,t];  s_c = mean_t |d[c,t]|;  z = clip(d/s_c, -ob, +ob)
+ * Only the columns the search fits are ever consumed (parrm.py:589-591), so the
+ * device path computes s_c in one streaming pass and gathers z at `indices`.
+ * ---------------------------------------------------------------------- */
+size_t parrm_channel_scales_workspace_bytes(int64_t n_chans, int64_t n_samples);
+/* d_scale[c] = mean |diff| of channel c (float64 regardless of dtype). */
+int parrm_channel_scales(const void* d_x, int64_t n_chans, int64_t n_samples, int64_t ld,
+                         double* d_scale, void* d_workspace, size_t workspace_bytes,
+                         int dtype, void* stream);
+/* d_y[c, j] = clip((x[c, idx_j + 1] - x[c, idx_j]) / scale[c]); also d_sumsq[c] = sum_j y^2
+ * (float64; may be NULL).  d_y is float64, SAMPLE-MAJOR: d_y[j * ld_y + c], ld_y >= n_chans
+ * (the layout the evaluator's shared-memory tiles want). */
+int parrm_standardise_gather(const void* d_x, int64_t n_chans, int64_t n_samples, int64_t ld,
+                             const int64_t* d_indices, int64_t n_indices,
+                             const double* d_scale, double outlier_boundary,
+                             double* d_y, int64_t ld_y, double* d_sumsq,
+                             int dtype, void* stream);
+/* Full z[c, 0..n_samples-2] (the `_standard_data` attribute), same dtype as x. */
+int parrm_standardise_full(const void* d_x, int64_t n_chans, int64_t n_samples, int64_t ld,
+                           const double* d_scale, double outlier_boundary,
+                           void* d_z, int64_t ld_z, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Period-candidate evaluator: PARRM._optimise_local + _fit_waves_to_data
+ * (parrm.py:552-632), batched over candidates (the pqdm map of parrm.py:445-454
+ * and the Nelder-Mead evaluations of parrm.py:499-517, 545-550).
+ *
+ * For every candidate p:  a_i = (idx_i + 1) * (2 pi / p);  W = [1, sin k a, cos k a]_{k<=bw};
+ * per channel beta = solve(W'W, W'y);  e_c = mean (y - W beta)^2 + sum_j lambda*j/sum(1..M) beta_j^2;
+ * fit_error[p] = sum_c e_c / n_chans_divisor;  +inf when the factorisation meets a zero pivot
+ * (the reference's LinAlgError -> inf, parrm.py:592-593, 627-628).
+ * ---------------------------------------------------------------------- */
+size_t parrm_eval_workspace_bytes(int64_t n_chans, int64_t n_indices, int64_t n_periods,
+                                  int bandwidth);
+int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
+                       const int64_t* d_indices, int64_t n_chans, int64_t n_indices,
+                       const double* d_periods, int64_t n_periods,
+                       int bandwidth, double lambda, int64_t n_chans_divisor,
+                       double* d_fit_error,
+                       void* d_workspace, size_t workspace_bytes, void* stream);
+/* First index of the smallest non-NaN value (NaN entries are skipped; all-NaN -> index 0). */
+int parrm_argmin(const double* d_values, int64_t n, double* d_min_value, int64_t* d_min_index,
+                 void* stream);
+
+/* ------------------------------------------------------------------------
+ * Tap builder: PARRM._generate_filter (parrm.py:803-833), integer-exact.
+ *   w in [-hw, hw] is a tap iff (mod(w, period) <= phw or >= period - phw) and |w| > omit,
+ *   "past" drops w > 0, "future" drops w <= 0.  mod is NumPy's (fmod + sign fix-up).
+ * d_taps (capacity 2*hw+1) receives the signed offsets ascending; *d_n_taps their count
+ * (0 = the reference's RuntimeError "A suitable filter cannot be created").
+ * ---------------------------------------------------------------------- */
+int parrm_build_taps(double period, double period_half_width, int64_t filter_half_width,
+                     int64_t omit_n_samples, int direction,
+                     int32_t* d_taps, int32_t* d_n_taps, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Filter application: body of PARRM.filter_data (parrm.py:861-869).
+ *   y[c,t] = x[c,t] - (1/n_in(t)) * sum_{w in taps, 0 <= t-w < T} x[c,t-w];  y = 0 where n_in(t) = 0
+ * (all tap weights are -1/n_taps, parrm.py:829, so the edge renormalisation of
+ *  parrm.py:861-866 reduces to the mean over the in-range taps).
+ *
+ * Time-chunk form (for halo'd shards): the output covers global times
+ * [t0, t0 + n_out) of a recording of n_samples_total samples; d_x holds global times
+ * [x_t0, x_t0 + n_x) and must contain every in-range sample the outputs touch, i.e.
+ * [max(0, t0 - w_max), min(T, t0 + n_out - w_min)).  For a whole recording pass
+ * x_t0 = t0 = 0 and n_x = n_out = n_samples_total.
+ *
+ * The tap list is passed as a "plan": an opaque relocatable blob that
+ * parrm_filter_plan() builds on the host from the ascending tap offsets (as produced by
+ * parrm_build_taps) and that the caller uploads verbatim; parrm_filter_apply() takes both
+ * the host copy (launch geometry) and the device copy (read by the kernels).
+ * ---------------------------------------------------------------------- */
+size_t parrm_filter_plan_bytes(int32_t n_taps);
+int parrm_filter_plan(const int32_t* h_taps, int32_t n_taps, int dtype,
+                      void* h_plan, size_t plan_bytes);
+int parrm_filter_apply(const void* d_x, int64_t ld_x, int64_t x_t0, int64_t n_x,
+                       void* d_out, int64_t ld_out, int64_t t0, int64_t n_out,
+                       int64_t n_samples_total, int64_t n_chans,
+                       const void* d_plan, const void* h_plan,
+                       int dtype, void* stream);
+
+/* Measured FP64 FMA throughput helper for the roofline denominator of the evaluator
+ * (bench.py): runs `iters` dependent-chain DFMA batches on every SM; reports flops issued. */
+int parrm_fp64_fma_burn(int64_t iters, double* d_sink, double* h_flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARRM_B200_H */

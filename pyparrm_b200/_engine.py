@@ -1,0 +1,525 @@
+"""Device engine: what ``pyparrm_b200.PARRM`` calls for every piece of arithmetic.
+
+One engine per process and GPU.  PyTorch owns device memory, pinned staging buffers and
+streams; all computation goes through the C ABI in ``_native`` (hand-written sm_100a
+kernels).  There is no CPU path: constructing the engine without a CUDA device raises.
+
+Host <-> device traffic uses a three-slot ring on three streams (H2D, compute, D2H), so the
+NumPy-in / NumPy-out API of the reference (``parrm.py:120-121``, ``:866-875``) overlaps copies
+with the kernels.  Pinned host arrays (see :func:`pinned_empty`) are copied directly; pageable
+ones are staged through pinned buffers with a threaded memcpy.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from concurrent.futures import ThreadPoolExecutor
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _native
+from ._native import check, lib
+
+_CHUNK_BYTES = int(os.environ.get("PYPARRM_B200_CHUNK_MB", "32")) << 20
+_PINNED_OUT_LIMIT = int(os.environ.get("PYPARRM_B200_PINNED_OUT_MB", "4096")) << 20
+_EVAL_WS_LIMIT = int(os.environ.get("PYPARRM_B200_EVAL_WS_MB", "1024")) << 20
+_N_SLOTS = 3
+_COPY_THREADS = max(1, min(8, (os.cpu_count() or 1)))
+_copy_pool: ThreadPoolExecutor | None = None
+
+
+def _vp(ptr: int) -> ctypes.c_void_p:
+    return ctypes.c_void_p(int(ptr))
+
+
+def _threaded_memmove(dst: int, src: int, nbytes: int) -> None:
+    """memcpy between host buffers on several threads (ctypes releases the GIL)."""
+    global _copy_pool
+    piece = 8 << 20
+    if nbytes <= piece or _COPY_THREADS == 1:
+        ctypes.memmove(dst, src, nbytes)
+        return
+    if _copy_pool is None:
+        _copy_pool = ThreadPoolExecutor(max_workers=_COPY_THREADS)
+    n_pieces = min(_COPY_THREADS, -(-nbytes // piece))
+    step = -(-nbytes // n_pieces)
+    step = (step + 63) & ~63
+    futures = []
+    for off in range(0, nbytes, step):
+        n = min(step, nbytes - off)
+        futures.append(_copy_pool.submit(ctypes.memmove, dst + off, src + off, n))
+    for f in futures:
+        f.result()
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """Uninitialised page-locked NumPy array (fast, asynchronous host<->device copies)."""
+    import torch
+
+    tdtype = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32}[
+        np.dtype(dtype)
+    ]
+    return torch.empty(tuple(shape), dtype=tdtype, pin_memory=True).numpy()
+
+
+def is_pinned(array: np.ndarray) -> bool:
+    return bool(lib.parrm_host_is_pinned(_vp(array.ctypes.data)))
+
+
+@dataclass
+class SearchTile:
+    """Standardised samples of one search run, resident on the device."""
+
+    y: object          # torch [n_indices, n_chans] float64, sample-major
+    sumsq: object      # torch [n_chans] float64
+    indices: object    # torch [n_indices] int64
+    n_indices: int
+    n_chans: int
+
+
+class DeviceEngine:
+    """All GPU work of the PARRM hot path for one device."""
+
+    def __init__(self, device: int | None = None):
+        import torch
+
+        if not torch.cuda.is_available() or _native.device_count() == 0:
+            raise RuntimeError(
+                "pyparrm_b200 needs an NVIDIA GPU (built for B200, sm_100a); no CUDA device is "
+                "visible and there is no CPU fallback."
+            )
+        self.torch = torch
+        index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", index)
+        with torch.cuda.device(self.device):
+            self.s_in = torch.cuda.Stream()
+            self.s_run = torch.cuda.Stream()
+            self.s_out = torch.cuda.Stream()
+        self._lock = threading.RLock()
+        self._ring = None          # (key, slots)
+        self._stage_in = None      # pinned staging for pageable inputs
+        self._stage_out = None
+        self._eval_ws = None
+        self._plans: dict = {}
+        self.launches = 0          # kernels of ours enqueued (bench.py reports it)
+
+    # ------------------------------------------------------------------ helpers
+    def _stream_ptr(self, stream) -> ctypes.c_void_p:
+        return _vp(stream.cuda_stream)
+
+    def _empty(self, n, dtype):
+        return self.torch.empty(int(n), dtype=dtype, device=self.device)
+
+    def _slots(self, in_bytes: int, out_bytes: int):
+        key = (in_bytes, out_bytes)
+        if self._ring is None or self._ring[0][0] < in_bytes or self._ring[0][1] < out_bytes:
+            t = self.torch
+            slots = []
+            for _ in range(_N_SLOTS):
+                slots.append(
+                    dict(
+                        d_in=self._empty(max(in_bytes, 16), t.uint8),
+                        d_out=self._empty(max(out_bytes, 16), t.uint8),
+                        ev_in=t.cuda.Event(),
+                        ev_run=t.cuda.Event(),
+                        ev_out=t.cuda.Event(),
+                        used=False,
+                    )
+                )
+            self._ring = (key, slots)
+        for slot in self._ring[1]:
+            slot["used"] = False
+        return self._ring[1]
+
+    def _staging(self, which: str, nbytes: int):
+        """Pinned host staging buffers (one per ring slot) for pageable arrays."""
+        t = self.torch
+        cur = getattr(self, which)
+        if cur is None or cur[0].numel() < nbytes:
+            cur = [t.empty(max(nbytes, 16), dtype=t.uint8, pin_memory=True) for _ in range(_N_SLOTS)]
+            setattr(self, which, cur)
+        return cur
+
+    # ------------------------------------------------------------- period search
+    def prepare_tiles(
+        self, data: np.ndarray, index_sets: list[np.ndarray], outlier_boundary: float
+    ) -> list[SearchTile]:
+        """Stream the recording through the device once: per-channel scale + gather.
+
+        Restates ``_standardise_data`` (parrm.py:272-280) restricted to the columns the search
+        reads (parrm.py:589-591), for every run's index set at once.
+        """
+        t = self.torch
+        data, dtype_code = self._as_float_array(data, allow_f32=True)
+        n_chans, n_samples = data.shape
+        elem = data.dtype.itemsize
+        with self._lock, t.cuda.device(self.device):
+            tiles = []
+            for idx in index_sets:
+                idx = np.ascontiguousarray(idx, dtype=np.int64)
+                if idx.size and (idx.min() < 0 or idx.max() > n_samples - 2):
+                    raise IndexError("search indices outside the differenced recording")
+                d_idx = t.from_numpy(idx).to(self.device)
+                tiles.append(
+                    SearchTile(
+                        y=t.empty((idx.shape[0], n_chans), dtype=t.float64, device=self.device),
+                        sumsq=t.empty(n_chans, dtype=t.float64, device=self.device),
+                        indices=d_idx,
+                        n_indices=int(idx.shape[0]),
+                        n_chans=int(n_chans),
+                    )
+                )
+            rows = max(1, _CHUNK_BYTES // max(1, n_samples * elem))
+            rows = min(rows, n_chans, 65535)
+            in_bytes = rows * n_samples * elem
+            slots = self._slots(in_bytes, 16)
+            ws_bytes = lib.parrm_channel_scales_workspace_bytes(rows, n_samples)
+            scale = t.empty(n_chans, dtype=t.float64, device=self.device)
+            ws = self._empty(max(ws_bytes, 16) * _N_SLOTS, t.uint8)
+            pinned = is_pinned(data)
+            stage = None if pinned else self._staging("_stage_in", in_bytes)
+            run = self._stream_ptr(self.s_run)
+            self.s_run.wait_stream(t.cuda.current_stream())
+            for i, c0 in enumerate(range(0, n_chans, rows)):
+                c1 = min(c0 + rows, n_chans)
+                slot = slots[i % _N_SLOTS]
+                nbytes = (c1 - c0) * n_samples * elem
+                src = data.ctypes.data + c0 * n_samples * elem
+                if slot["used"]:
+                    slot["ev_run"].synchronize()  # kernels done with d_in (and staging reusable)
+                if not pinned:
+                    _threaded_memmove(stage[i % _N_SLOTS].data_ptr(), src, nbytes)
+                    src = stage[i % _N_SLOTS].data_ptr()
+                check(lib.parrm_copy_h2d_async(_vp(slot["d_in"].data_ptr()), _vp(src), nbytes,
+                                               self._stream_ptr(self.s_in)), "H2D copy")
+                slot["ev_in"].record(self.s_in)
+                self.s_run.wait_event(slot["ev_in"])
+                ws_ptr = ws.data_ptr() + (i % _N_SLOTS) * max(ws_bytes, 16)
+                check(lib.parrm_channel_scales(
+                    _vp(slot["d_in"].data_ptr()), c1 - c0, n_samples, n_samples,
+                    _vp(scale.data_ptr() + 8 * c0), _vp(ws_ptr), ws_bytes, dtype_code, run),
+                    "parrm_channel_scales")
+                self.launches += 2
+                for tile in tiles:
+                    check(lib.parrm_standardise_gather(
+                        _vp(slot["d_in"].data_ptr()), c1 - c0, n_samples, n_samples,
+                        _vp(tile.indices.data_ptr()), tile.n_indices,
+                        _vp(scale.data_ptr() + 8 * c0), float(outlier_boundary),
+                        _vp(tile.y.data_ptr() + 8 * c0), n_chans,
+                        _vp(tile.sumsq.data_ptr() + 8 * c0), dtype_code, run),
+                        "parrm_standardise_gather")
+                    self.launches += 2
+                slot["ev_run"].record(self.s_run)
+                slot["used"] = True
+            self.s_run.synchronize()
+            self._scale = scale
+            return tiles
+
+    def tile_from_standardised(self, z: np.ndarray, indices: np.ndarray) -> SearchTile:
+        """Tile from an already standardised ``[channels, times]`` host array (the reference's
+        ``_optimise_local(period, data, indices, ...)`` seam, parrm.py:552-559)."""
+        t = self.torch
+        indices = np.ascontiguousarray(indices, dtype=np.int64)
+        y = np.ascontiguousarray(z[:, indices].T, dtype=np.float64)
+        with self._lock, t.cuda.device(self.device):
+            d_y = t.from_numpy(y).to(self.device)
+            return SearchTile(
+                y=d_y, sumsq=(d_y * d_y).sum(0), indices=t.from_numpy(indices).to(self.device),
+                n_indices=int(y.shape[0]), n_chans=int(y.shape[1]),
+            )
+
+    def standardise_full(self, data: np.ndarray, outlier_boundary: float) -> np.ndarray:
+        """The reference's ``_standard_data`` array [C, T-1] (parrm.py:272-280), on demand."""
+        t = self.torch
+        data, dtype_code = self._as_float_array(data, allow_f32=True)
+        n_chans, n_samples = data.shape
+        out = np.empty((n_chans, n_samples - 1), dtype=data.dtype)
+        tdtype = t.float64 if dtype_code == _native.F64 else t.float32
+        rows = max(1, min(n_chans, 65535, _CHUNK_BYTES // max(1, n_samples * data.dtype.itemsize)))
+        with self._lock, t.cuda.device(self.device):
+            stream = t.cuda.current_stream()
+            sp = self._stream_ptr(stream)
+            for c0 in range(0, n_chans, rows):
+                c1 = min(c0 + rows, n_chans)
+                d_x = t.from_numpy(np.ascontiguousarray(data[c0:c1])).to(self.device)
+                scale = t.empty(c1 - c0, dtype=t.float64, device=self.device)
+                ws_bytes = lib.parrm_channel_scales_workspace_bytes(c1 - c0, n_samples)
+                ws = self._empty(max(ws_bytes, 16), t.uint8)
+                check(lib.parrm_channel_scales(_vp(d_x.data_ptr()), c1 - c0, n_samples, n_samples,
+                                               _vp(scale.data_ptr()), _vp(ws.data_ptr()), ws_bytes,
+                                               dtype_code, sp), "parrm_channel_scales")
+                d_z = t.empty((c1 - c0, n_samples - 1), dtype=tdtype, device=self.device)
+                check(lib.parrm_standardise_full(_vp(d_x.data_ptr()), c1 - c0, n_samples,
+                                                 n_samples, _vp(scale.data_ptr()),
+                                                 float(outlier_boundary), _vp(d_z.data_ptr()),
+                                                 n_samples - 1, dtype_code, sp),
+                      "parrm_standardise_full")
+                self.launches += 3
+                out[c0:c1] = d_z.cpu().numpy()
+        return out
+
+    def evaluate(
+        self,
+        tile: SearchTile,
+        periods: np.ndarray,
+        bandwidth: int,
+        lambda_: float,
+        n_chans_divisor: int,
+    ) -> np.ndarray:
+        """Objective of ``_optimise_local`` (parrm.py:552-597) for every candidate period."""
+        periods = np.ascontiguousarray(periods, dtype=np.float64).ravel()
+        n_periods = int(periods.shape[0])
+        if n_periods == 0:
+            return np.zeros(0, dtype=np.float64)
+        d_err = self.evaluate_device(tile, periods, bandwidth, lambda_, n_chans_divisor)
+        return d_err.cpu().numpy()
+
+    def evaluate_device(self, tile, periods, bandwidth, lambda_, n_chans_divisor):
+        """Like :meth:`evaluate`, but ``periods`` may be a device tensor and so is the result."""
+        t = self.torch
+        bandwidth = int(bandwidth)
+        if bandwidth > _native.MAX_BANDWIDTH:
+            raise ValueError(f"bandwidth {bandwidth} exceeds the device limit {_native.MAX_BANDWIDTH}")
+        with self._lock, t.cuda.device(self.device):
+            if isinstance(periods, np.ndarray):
+                d_per = t.from_numpy(np.ascontiguousarray(periods, dtype=np.float64)).to(self.device)
+            else:
+                d_per = periods.to(device=self.device, dtype=t.float64).contiguous()
+            n_periods = int(d_per.shape[0])
+            d_err = t.empty(n_periods, dtype=t.float64, device=self.device)
+            per_cand = max(
+                1, lib.parrm_eval_workspace_bytes(tile.n_chans, tile.n_indices, 1, bandwidth)
+            )
+            batch = max(1, min(n_periods, _EVAL_WS_LIMIT // per_cand))
+            # workspace size is not linear in the batch (sample splits shrink as it grows)
+            ws_bytes = max(
+                lib.parrm_eval_workspace_bytes(tile.n_chans, tile.n_indices, b, bandwidth)
+                for b in {batch, min(batch, n_periods % batch or batch)}
+            )
+            if self._eval_ws is None or self._eval_ws.numel() < ws_bytes:
+                self._eval_ws = self._empty(ws_bytes, t.uint8)
+            sp = self._stream_ptr(t.cuda.current_stream())
+            for p0 in range(0, n_periods, batch):
+                p1 = min(p0 + batch, n_periods)
+                need = lib.parrm_eval_workspace_bytes(tile.n_chans, tile.n_indices, p1 - p0, bandwidth)
+                if self._eval_ws.numel() < need:
+                    self._eval_ws = self._empty(need, t.uint8)
+                check(lib.parrm_eval_periods(
+                    _vp(tile.y.data_ptr()), tile.n_chans, _vp(tile.sumsq.data_ptr()),
+                    _vp(tile.indices.data_ptr()), tile.n_chans, tile.n_indices,
+                    _vp(d_per.data_ptr() + 8 * p0), p1 - p0, bandwidth, float(lambda_),
+                    int(n_chans_divisor), _vp(d_err.data_ptr() + 8 * p0),
+                    _vp(self._eval_ws.data_ptr()), self._eval_ws.numel(), sp),
+                    "parrm_eval_periods")
+                self.launches += 2
+            return d_err
+
+    def argmin(self, d_values):
+        """(min value, first index) of a device vector, NaNs skipped (on device)."""
+        t = self.torch
+        with self._lock, t.cuda.device(self.device):
+            d_val = t.empty(1, dtype=t.float64, device=self.device)
+            d_idx = t.empty(1, dtype=t.int64, device=self.device)
+            check(lib.parrm_argmin(_vp(d_values.data_ptr()), int(d_values.shape[0]),
+                                   _vp(d_val.data_ptr()), _vp(d_idx.data_ptr()),
+                                   self._stream_ptr(t.cuda.current_stream())), "parrm_argmin")
+            self.launches += 1
+            return float(d_val.item()), int(d_idx.item())
+
+    # --------------------------------------------------------------------- taps
+    def build_taps(
+        self, period: float, period_half_width: float, filter_half_width: int,
+        omit_n_samples: int, direction: str,
+    ) -> np.ndarray:
+        """Tap offsets of ``_generate_filter`` (parrm.py:803-820), ascending int32."""
+        t = self.torch
+        with self._lock, t.cuda.device(self.device):
+            d_taps = t.empty(2 * int(filter_half_width) + 1, dtype=t.int32, device=self.device)
+            d_n = t.zeros(1, dtype=t.int32, device=self.device)
+            check(lib.parrm_build_taps(
+                float(period), float(period_half_width), int(filter_half_width),
+                int(omit_n_samples), _native.DIRECTIONS[direction], _vp(d_taps.data_ptr()),
+                _vp(d_n.data_ptr()), self._stream_ptr(t.cuda.current_stream())),
+                "parrm_build_taps")
+            self.launches += 1
+            n = int(d_n.item())
+            return d_taps[:n].cpu().numpy()
+
+    # ------------------------------------------------------------------- filter
+    def _plan(self, taps: np.ndarray, dtype_code: int):
+        """Host + device copies of the filter plan for a tap list (small LRU cache)."""
+        t = self.torch
+        taps = np.ascontiguousarray(taps, dtype=np.int32)
+        key = (dtype_code, taps.tobytes())
+        hit = self._plans.get(key)
+        if hit is not None:
+            return hit
+        nbytes = lib.parrm_filter_plan_bytes(int(taps.shape[0]))
+        h_plan = np.zeros(nbytes, dtype=np.uint8)
+        check(lib.parrm_filter_plan(_vp(taps.ctypes.data), int(taps.shape[0]), dtype_code,
+                                    _vp(h_plan.ctypes.data), nbytes), "parrm_filter_plan")
+        d_plan = t.from_numpy(h_plan).to(self.device)
+        if len(self._plans) >= 16:
+            self._plans.pop(next(iter(self._plans)))
+        span = (min(int(taps[0]), 0), max(int(taps[-1]), 0))
+        self._plans[key] = (h_plan, d_plan, span)
+        return self._plans[key]
+
+    def _as_float_array(self, data: np.ndarray, allow_f32: bool):
+        if data.dtype == np.float64:
+            code = _native.F64
+        elif data.dtype == np.float32 and allow_f32:
+            code = _native.F32
+        elif np.issubdtype(data.dtype, np.floating) or np.issubdtype(data.dtype, np.integer) \
+                or data.dtype == np.bool_:
+            data, code = data.astype(np.float64), _native.F64
+        else:
+            raise TypeError(f"unsupported data dtype {data.dtype}")
+        if not data.flags.c_contiguous:
+            data = np.ascontiguousarray(data)
+        return data, code
+
+    def filter_device(self, d_x, taps: np.ndarray, d_out=None, stream=None):
+        """Filter a device-resident [C, T] tensor (float64 or float32); returns a device tensor."""
+        t = self.torch
+        code = {t.float64: _native.F64, t.float32: _native.F32}[d_x.dtype]
+        if d_x.dim() != 2 or d_x.stride(1) != 1:
+            raise ValueError("device input must be a 2-D row-major tensor")
+        n_chans, n_samples = d_x.shape
+        h_plan, d_plan, _ = self._plan(taps, code)
+        if d_out is None:
+            d_out = t.empty((n_chans, n_samples), dtype=d_x.dtype, device=d_x.device)
+        stream = stream or t.cuda.current_stream()
+        for c0 in range(0, n_chans, 65535):
+            c1 = min(c0 + 65535, n_chans)
+            check(lib.parrm_filter_apply(
+                _vp(d_x[c0:c1].data_ptr()), d_x.stride(0), 0, n_samples,
+                _vp(d_out[c0:c1].data_ptr()), d_out.stride(0), 0, n_samples, n_samples, c1 - c0,
+                _vp(d_plan.data_ptr()), _vp(h_plan.ctypes.data), code, self._stream_ptr(stream)),
+                "parrm_filter_apply")
+            self.launches += 1
+        return d_out
+
+    def filter_host(self, data: np.ndarray, taps: np.ndarray, precision: str = "fp64") -> np.ndarray:
+        """``filter_data`` body (parrm.py:861-869): NumPy [C, T] in, float64 NumPy [C, T] out."""
+        t = self.torch
+        data, _ = self._as_float_array(data, allow_f32=False)
+        n_chans, n_samples = data.shape
+        out_bytes_total = n_chans * n_samples * 8
+        if 0 < out_bytes_total <= _PINNED_OUT_LIMIT:
+            out = pinned_empty((n_chans, n_samples), np.float64)
+        else:
+            out = np.empty((n_chans, n_samples), dtype=np.float64)
+        if n_chans == 0 or n_samples == 0:
+            return out
+        compute_f32 = precision == "fp32"
+        code = _native.F32 if compute_f32 else _native.F64
+        with self._lock, t.cuda.device(self.device):
+            h_plan, d_plan, (w_lo, w_hi) = self._plan(taps, code)
+            span = w_hi - w_lo
+            row_bytes = n_samples * 8
+            # chunk list: (c0, c1, t0, t1, x0, x1) -- channels [c0,c1), outputs [t0,t1), inputs [x0,x1)
+            chunks = []
+            if row_bytes <= 2 * _CHUNK_BYTES:
+                rows = max(1, min(n_chans, 65535, _CHUNK_BYTES // row_bytes))
+                for c0 in range(0, n_chans, rows):
+                    chunks.append((c0, min(c0 + rows, n_chans), 0, n_samples, 0, n_samples))
+            else:
+                step = max(_CHUNK_BYTES // 8, 4 * span)
+                for c in range(n_chans):
+                    for t0 in range(0, n_samples, step):
+                        t1 = min(t0 + step, n_samples)
+                        chunks.append((c, c + 1, t0, t1, max(0, t0 - w_hi), min(n_samples, t1 - w_lo)))
+            in_bytes = max((c1 - c0) * (x1 - x0) * 8 for c0, c1, _, _, x0, x1 in chunks)
+            out_bytes = max((c1 - c0) * (t1 - t0) * 8 for c0, c1, t0, t1, _, _ in chunks)
+            slots = self._slots(in_bytes, out_bytes)
+            in_pinned, out_pinned = is_pinned(data), is_pinned(out)
+            stage_in = None if in_pinned else self._staging("_stage_in", in_bytes)
+            stage_out = None if out_pinned else self._staging("_stage_out", out_bytes)
+            s_in, s_run, s_out = (self._stream_ptr(s) for s in (self.s_in, self.s_run, self.s_out))
+            pending = [None] * _N_SLOTS  # (host dst ptr, nbytes) awaiting copy-out of staging
+            tf32 = [None] * _N_SLOTS
+
+            def drain(k):
+                if pending[k] is not None:
+                    slots[k]["ev_out"].synchronize()
+                    dst, nbytes = pending[k]
+                    _threaded_memmove(dst, stage_out[k].data_ptr(), nbytes)
+                    pending[k] = None
+
+            for i, (c0, c1, t0, t1, x0, x1) in enumerate(chunks):
+                k = i % _N_SLOTS
+                slot = slots[k]
+                n_c, n_x, n_o = c1 - c0, x1 - x0, t1 - t0
+                src = data.ctypes.data + (c0 * n_samples + x0) * 8
+                dst = out.ctypes.data + (c0 * n_samples + t0) * 8
+                if slot["used"]:
+                    if not in_pinned:
+                        slot["ev_in"].synchronize()  # staging buffer free again
+                    drain(k)
+                if not in_pinned:
+                    _threaded_memmove(stage_in[k].data_ptr(), src, n_c * n_x * 8)
+                    src = stage_in[k].data_ptr()
+                if slot["used"]:
+                    self.s_in.wait_event(slot["ev_run"])   # kernel finished reading d_in
+                check(lib.parrm_copy_h2d_async(_vp(slot["d_in"].data_ptr()), _vp(src),
+                                               n_c * n_x * 8, s_in), "H2D copy")
+                slot["ev_in"].record(self.s_in)
+                self.s_run.wait_event(slot["ev_in"])
+                if slot["used"]:
+                    self.s_run.wait_event(slot["ev_out"])  # previous result left d_out
+                d_in_ptr, d_out_ptr = slot["d_in"].data_ptr(), slot["d_out"].data_ptr()
+                if compute_f32:
+                    with t.cuda.stream(self.s_run):
+                        x64 = slot["d_in"][: n_c * n_x * 8].view(t.float64)
+                        x32 = x64.to(t.float32)
+                        y32 = t.empty(n_c * n_o, dtype=t.float32, device=self.device)
+                        tf32[k] = (x32, y32)
+                    d_in_ptr, d_out_ptr = x32.data_ptr(), y32.data_ptr()
+                check(lib.parrm_filter_apply(
+                    _vp(d_in_ptr), n_x, x0, n_x, _vp(d_out_ptr), n_o, t0, n_o, n_samples, n_c,
+                    _vp(d_plan.data_ptr()), _vp(h_plan.ctypes.data), code, s_run),
+                    "parrm_filter_apply")
+                self.launches += 1
+                if compute_f32:
+                    with t.cuda.stream(self.s_run):
+                        slot["d_out"][: n_c * n_o * 8].view(t.float64).copy_(tf32[k][1])
+                slot["ev_run"].record(self.s_run)
+                self.s_out.wait_event(slot["ev_run"])
+                if out_pinned:
+                    check(lib.parrm_copy_d2h_async(_vp(dst), _vp(slot["d_out"].data_ptr()),
+                                                   n_c * n_o * 8, s_out), "D2H copy")
+                else:
+                    check(lib.parrm_copy_d2h_async(_vp(stage_out[k].data_ptr()),
+                                                   _vp(slot["d_out"].data_ptr()), n_c * n_o * 8,
+                                                   s_out), "D2H copy")
+                    pending[k] = (dst, n_c * n_o * 8)
+                slot["ev_out"].record(self.s_out)
+                slot["used"] = True
+            for k in range(_N_SLOTS):
+                drain(k)
+            self.s_out.synchronize()
+        return out
+
+
+_engine: DeviceEngine | None = None
+_engine_lock = threading.Lock()
+
+
+def get_engine() -> DeviceEngine:
+    """Process-wide engine for the current CUDA device (created on first use)."""
+    global _engine
+    with _engine_lock:
+        if _engine is None:
+            _engine = DeviceEngine()
+        return _engine
+
+
+def set_engine(engine) -> None:
+    """Install an engine object (tests inject a stand-in; ``None`` resets)."""
+    global _engine
+    with _engine_lock:
+        _engine = engine

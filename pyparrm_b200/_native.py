@@ -1,0 +1,102 @@
+"""ctypes binding of ``libparrm_b200.so`` (C ABI declared in ``include/parrm_b200.h``).
+
+The library is built in-tree by ``pyparrm_b200/csrc/build.sh`` (``__graft_entry__.build``).
+There is no fallback: if the shared object is missing, importing this module raises, and
+every compute entry point raises ``RuntimeError`` with the library's own message when the
+CUDA call behind it fails (e.g. on a host without a GPU).
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+LIB_NAME = "libparrm_b200.so"
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+
+F64, F32 = 0, 1
+DIR_BOTH, DIR_PAST, DIR_FUTURE = 0, 1, 2
+DIRECTIONS = {"both": DIR_BOTH, "past": DIR_PAST, "future": DIR_FUTURE}
+MAX_BANDWIDTH = 23
+ABI_VERSION = 1
+
+# name -> (restype, argtypes); mirrors include/parrm_b200.h one to one
+SIGNATURES = {
+    "parrm_abi_version": (c_int, []),
+    "parrm_last_error": (c_char_p, []),
+    "parrm_device_count": (c_int, []),
+    "parrm_host_is_pinned": (c_int, [c_void_p]),
+    "parrm_copy_h2d_async": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "parrm_copy_d2h_async": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "parrm_channel_scales_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "parrm_channel_scales": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_int, c_void_p],
+    ),
+    "parrm_standardise_gather": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_double,
+         c_void_p, c_int64, c_void_p, c_int, c_void_p],
+    ),
+    "parrm_standardise_full": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_double, c_void_p, c_int64, c_int,
+         c_void_p],
+    ),
+    "parrm_eval_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
+    "parrm_eval_periods": (
+        c_int,
+        [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int,
+         c_double, c_int64, c_void_p, c_void_p, c_size_t, c_void_p],
+    ),
+    "parrm_argmin": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "parrm_build_taps": (
+        c_int, [c_double, c_double, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]
+    ),
+    "parrm_filter_plan_bytes": (c_size_t, [c_int32]),
+    "parrm_filter_plan": (c_int, [c_void_p, c_int32, c_int, c_void_p, c_size_t]),
+    "parrm_filter_apply": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
+         c_int64, c_void_p, c_void_p, c_int, c_void_p],
+    ),
+    "parrm_fp64_fma_burn": (c_int, [c_int64, c_void_p, POINTER(c_double), c_void_p]),
+}
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_NAME} is not built (expected {LIB_PATH}). Build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` or "
+            "`pyparrm_b200/csrc/build.sh`. pyparrm_b200 has no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.parrm_abi_version() != ABI_VERSION:
+        raise ImportError(
+            f"{LIB_NAME} has ABI version {lib.parrm_abi_version()}, expected {ABI_VERSION}; rebuild it."
+        )
+    return lib
+
+
+lib = _load()
+
+
+def last_error() -> str:
+    msg = lib.parrm_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(status: int, what: str) -> None:
+    """Raise if a C-ABI call did not return PARRM_OK."""
+    if status != 0:
+        raise RuntimeError(f"{what} failed (status {status}): {last_error()}")
+
+
+def device_count() -> int:
+    return int(lib.parrm_device_count())

@@ -1,0 +1,526 @@
+// Period-candidate evaluator: PARRM._optimise_local / _fit_waves_to_data (parrm.py:552-632),
+// batched over candidate periods.
+//
+// Reference, per candidate p and channel c (N fitted samples, M = 2*bw + 1):
+//     a_i = (idx_i + 1) * (2 pi / p);   W = [1, sin(k a_i), cos(k a_i)]_{k=1..bw}      (N x M)
+//     beta = solve(W'W, W'y_c);  e_c = mean_i (y_c - W beta)_i^2 + sum_j lambda*j/sum(1..M) * beta_j^2
+//     fit_error(p) = sum_c e_c / n_chans
+//
+// Device formulation (one pass over the samples, no N x M matrix ever stored):
+//   * the Gram matrix W'W does not depend on the channel (the reference rebuilds it per
+//     channel) and, by the product-to-sum identities, is a linear function of the 4*bw+1
+//     harmonic sums  C_m = sum_i cos(m a_i),  S_m = sum_i sin(m a_i),  m = 0..2*bw;
+//   * the right-hand sides are one small GEMM  B = W' Y  (M x C, K = N);
+//   * with beta solving the normal equations,  sum_i (y - W beta)_i^2 = y'y - beta' W'y.
+// Kernel 1 (accumulate) walks the samples: one accurate sincos(a_i) per sample, harmonics by
+// the angle-addition recurrence in registers, harmonic sums in registers, and a register-tiled
+// FP64 FMA GEMM from shared-memory tiles for B.  Samples can be split over several CTAs per
+// candidate (few candidates, e.g. Nelder-Mead steps); partials are combined in a fixed order.
+// Kernel 2 (solve) assembles the Gram matrix, factorises it with partial pivoting (zero pivot
+// -> +inf, the reference's LinAlgError path), solves all channels and reduces the objective.
+#include "common.cuh"
+
+namespace parrm {
+
+constexpr int kAccThreads = 256;
+constexpr int kSuper = 256;       // samples per sincos batch (one per thread)
+constexpr int kKT = 64;           // samples per GEMM tile
+constexpr int kGroups = 4;        // harmonic groups per sample (kGroups * kKT == kAccThreads)
+constexpr int kHMax = (2 * PARRM_MAX_BANDWIDTH + kGroups - 1) / kGroups;  // 12
+constexpr int kMaxRows = 2 * PARRM_MAX_BANDWIDTH + 1;                     // 47
+constexpr int kRowsPad = 48;      // padded design-matrix row: 8 row groups x 6
+constexpr int kRowTile = 6;
+static_assert(kMaxRows <= kRowsPad, "row groups must cover the widest design matrix");
+constexpr int kColTile = 4;
+constexpr int kChanTile = 64;     // channels per CTA (16 column groups x 4)
+constexpr int kHalf = 128;        // threads per K-half
+
+struct EvalShape {
+  int64_t n_chans, n_indices, n_periods;
+  int bandwidth, n_rows;          // n_rows = 2*bw + 1
+  int n_splits, n_chan_tiles;
+  int64_t split_len;              // samples per split (multiple of kSuper)
+  int64_t ld_y;
+  // workspace layout (doubles)
+  int64_t b_stride_split;         // n_rows * n_chans
+  int64_t b_stride_period;        // 2 * n_splits * b_stride_split   (two K-halves per split)
+  int64_t t_stride_split;         // 4 * bw   (C_1..C_2bw, S_1..S_2bw)
+  int64_t t_stride_period;        // n_splits * t_stride_split
+  int64_t t_offset;               // start of the harmonic-sum area
+};
+
+__device__ __forceinline__ void cmul(double& c, double& s, double c2, double s2) {
+  const double nc = fma(c, c2, -(s * s2));
+  const double ns = fma(s, c2, c * s2);
+  c = nc;
+  s = ns;
+}
+
+// (c, s) = (c1 + i s1)^n by binary powering
+__device__ __forceinline__ void cpow(double c1, double s1, int n, double& c, double& s) {
+  c = 1.0;
+  s = 0.0;
+  double bc = c1, bs = s1;
+  while (n > 0) {
+    if (n & 1) cmul(c, s, bc, bs);
+    n >>= 1;
+    if (n) cmul(bc, bs, bc, bs);
+  }
+}
+
+__global__ void __launch_bounds__(kAccThreads, 2)
+eval_accumulate_kernel(const double* __restrict__ y, const int64_t* __restrict__ indices,
+                       const double* __restrict__ periods, double* __restrict__ ws,
+                       const EvalShape sh) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* s_cs = reinterpret_cast<double2*>(smem_raw);                 // [kSuper] (cos, sin)
+  double* s_w = reinterpret_cast<double*>(smem_raw + kSuper * 16);      // [kKT][kRowsPad]
+  double* s_y = s_w + kKT * kRowsPad;                                   // [kKT][kChanTile]
+  double* s_red = s_y + kKT * kChanTile;                                // [8 warps][2*H]
+  constexpr int H = kHMax;
+
+  const int tid = threadIdx.x;
+  const int64_t cand = blockIdx.x;
+  const int split = blockIdx.y;
+  const int ctile = blockIdx.z;
+  const int bw = sh.bandwidth, two_bw = 2 * bw;
+  const int n_rows = sh.n_rows;
+  const int64_t n_begin = int64_t(split) * sh.split_len;
+  const int64_t n_end = min(n_begin + sh.split_len, sh.n_indices);
+  const int chan0 = ctile * kChanTile;
+  const int n_chan_here = int(min64(kChanTile, sh.n_chans - chan0));
+  const double delta = 6.283185307179586 / periods[cand];  // 2*pi/period (parrm.py:619)
+
+  // generator role: sample lane gi, harmonic group gg -> harmonics gg*h+1 .. gg*h+h
+  const int gi = tid & (kKT - 1), gg = tid / kKT;
+  const int h = (two_bw + kGroups - 1) / kGroups;
+  const int m0 = gg * h;
+  double sum_c[H], sum_s[H];
+#pragma unroll
+  for (int j = 0; j < H; ++j) sum_c[j] = sum_s[j] = 0.0;
+
+  // GEMM role: K-half kh, row group rg (6 rows), column group cg (4 channels)
+  const int kh = tid / kHalf, th = tid % kHalf;
+  const int rg = th / 16, cg = th % 16;
+  const bool rows_live = rg * kRowTile < n_rows;
+  double acc[kRowTile][kColTile];
+#pragma unroll
+  for (int r = 0; r < kRowTile; ++r)
+#pragma unroll
+    for (int c = 0; c < kColTile; ++c) acc[r][c] = 0.0;
+
+  for (int64_t n_super = n_begin; n_super < n_end; n_super += kSuper) {
+    // one accurate sincos per sample of this batch; invalid lanes hold (0, 0)
+    {
+      const int64_t n = n_super + tid;
+      double2 cs = make_double2(0.0, 0.0);
+      if (n < n_end) {
+        const double angle = double(indices[n] + 1) * delta;
+        sincos(angle, &cs.y, &cs.x);
+      }
+      s_cs[tid] = cs;
+    }
+    __syncthreads();
+    for (int sub = 0; sub < kSuper / kKT; ++sub) {
+      const int64_t n_tile = n_super + sub * kKT;
+      if (n_tile >= n_end) break;  // uniform
+      // ---- generate harmonics of kKT samples ----
+      {
+        const int64_t n = n_tile + gi;
+        const bool live = n < n_end;
+        const double2 cs1 = s_cs[sub * kKT + gi];
+        double c, s;
+        cpow(cs1.x, cs1.y, m0, c, s);
+        double* wrow = s_w + gi * kRowsPad;
+        if (gg == 0) wrow[0] = live ? 1.0 : 0.0;
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+          if (j >= h) break;  // uniform
+          cmul(c, s, cs1.x, cs1.y);
+          const int m = m0 + j + 1;
+          if (m <= two_bw && live) {
+            sum_c[j] += c;
+            sum_s[j] += s;
+          }
+          if (m <= bw) {  // columns 2m-1 = sin, 2m = cos (parrm.py:622-623)
+            wrow[2 * m - 1] = live ? s : 0.0;
+            wrow[2 * m] = live ? c : 0.0;
+          }
+        }
+        // zero the padding rows once per tile so the FMA tiles can run unmasked
+        if (gg == kGroups - 1)
+          for (int r = n_rows; r < kRowsPad; ++r) wrow[r] = 0.0;
+      }
+      // ---- stage the Y tile (sample-major rows of n_chan_here doubles) ----
+      for (int e = tid; e < kKT * kChanTile; e += kAccThreads) {
+        const int k = e / kChanTile, c = e % kChanTile;
+        const int64_t n = n_tile + k;
+        s_y[e] = (n < n_end && c < n_chan_here) ? y[n * sh.ld_y + chan0 + c] : 0.0;
+      }
+      __syncthreads();
+      // ---- B += W' Y over this K-half's 32 samples ----
+      if (rows_live) {
+        const double* wp = s_w + (kh * (kKT / 2)) * kRowsPad + rg * kRowTile;
+        const double* yp = s_y + (kh * (kKT / 2)) * kChanTile + cg * kColTile;
+#pragma unroll 4
+        for (int k = 0; k < kKT / 2; ++k) {
+          const double2 w01 = *reinterpret_cast<const double2*>(wp + k * kRowsPad);
+          const double2 w23 = *reinterpret_cast<const double2*>(wp + k * kRowsPad + 2);
+          const double2 w45 = *reinterpret_cast<const double2*>(wp + k * kRowsPad + 4);
+          const double2 y01 = *reinterpret_cast<const double2*>(yp + k * kChanTile);
+          const double2 y23 = *reinterpret_cast<const double2*>(yp + k * kChanTile + 2);
+          const double wv[kRowTile] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y};
+          const double yv[kColTile] = {y01.x, y01.y, y23.x, y23.y};
+#pragma unroll
+          for (int r = 0; r < kRowTile; ++r)
+#pragma unroll
+            for (int c = 0; c < kColTile; ++c) acc[r][c] = fma(wv[r], yv[c], acc[r][c]);
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- write the B partial of this (candidate, split, K-half) ----
+  {
+    double* bp = ws + cand * sh.b_stride_period + (int64_t(split) * 2 + kh) * sh.b_stride_split;
+#pragma unroll
+    for (int r = 0; r < kRowTile; ++r) {
+      const int row = rg * kRowTile + r;
+      if (row < n_rows) {
+#pragma unroll
+        for (int c = 0; c < kColTile; ++c) {
+          const int ch = cg * kColTile + c;
+          if (ch < n_chan_here) bp[int64_t(row) * sh.n_chans + chan0 + ch] = acc[r][c];
+        }
+      }
+    }
+  }
+  // ---- harmonic sums: reduce the kKT sample lanes of each group (channel tile 0 only) ----
+  if (ctile == 0) {
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+      const double c = warp_sum(sum_c[j]);
+      const double s = warp_sum(sum_s[j]);
+      if (lane == 0) {
+        s_red[warp * 2 * H + j] = c;
+        s_red[warp * 2 * H + H + j] = s;
+      }
+    }
+    __syncthreads();
+    // kKT/32 = 2 warps per group: warps 2g and 2g+1
+    double* tp = ws + sh.t_offset + cand * sh.t_stride_period + int64_t(split) * sh.t_stride_split;
+    for (int e = tid; e < kGroups * H; e += kAccThreads) {
+      const int g = e / H, j = e % H;
+      const int m = g * h + j + 1;
+      if (j < h && m <= two_bw) {
+        tp[m - 1] = s_red[(2 * g) * 2 * H + j] + s_red[(2 * g + 1) * 2 * H + j];
+        tp[two_bw + m - 1] = s_red[(2 * g) * 2 * H + H + j] + s_red[(2 * g + 1) * 2 * H + H + j];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+constexpr int kSolveThreads = 128;
+constexpr int kGStride = kMaxRows + 1;  // row stride of the Gram matrix
+
+__global__ void __launch_bounds__(kSolveThreads)
+eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sumsq, double lambda,
+                  int64_t n_chans_divisor, double* __restrict__ fit_error, const EvalShape sh) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int M = sh.n_rows, bw = sh.bandwidth, two_bw = 2 * bw;
+  double* s_g = reinterpret_cast<double*>(smem_raw);   // [M][kGStride] LU factors
+  double* s_hc = s_g + kMaxRows * kGStride;   // C_0..C_2bw
+  double* s_hs = s_hc + kMaxRows;             // S_0..S_2bw
+  double* s_b = s_hs + kMaxRows;              // [M][kSolveThreads] right-hand sides
+  double* s_x = s_b + kMaxRows * kSolveThreads;  // [M][kSolveThreads] work / solution
+  __shared__ int s_perm[kMaxRows];
+  __shared__ int s_piv;
+  __shared__ int s_singular;
+  __shared__ double s_part[kSolveThreads / 32];
+
+  const int tid = threadIdx.x;
+  const int64_t cand = blockIdx.x;
+
+  // harmonic sums, splits added in a fixed order
+  for (int e = tid; e <= two_bw; e += kSolveThreads) {
+    double c = 0.0, s = 0.0;
+    if (e == 0) {
+      c = double(sh.n_indices);
+    } else {
+      const double* tp = ws + sh.t_offset + cand * sh.t_stride_period;
+      for (int sp = 0; sp < sh.n_splits; ++sp) {
+        c += tp[sp * sh.t_stride_split + e - 1];
+        s += tp[sp * sh.t_stride_split + two_bw + e - 1];
+      }
+    }
+    s_hc[e] = c;
+    s_hs[e] = s;
+  }
+  if (tid == 0) s_singular = 0;
+  __syncthreads();
+  // Gram matrix by product-to-sum: column 0 = 1, 2k-1 = sin(k a), 2k = cos(k a)
+  for (int e = tid; e < M * M; e += kSolveThreads) {
+    const int i = e / M, j = e % M;
+    const int ki = (i + 1) / 2, kj = (j + 1) / 2;      // harmonic numbers (0 for the constant)
+    const bool si = (i & 1), sj = (j & 1);             // odd column = sine
+    const int kd = ki > kj ? ki - kj : kj - ki, ksum = ki + kj;
+    double v;
+    if (i == 0 && j == 0) {
+      v = s_hc[0];
+    } else if (i == 0 || j == 0) {
+      const int k = ki + kj;
+      v = (si || sj) ? s_hs[k] : s_hc[k];
+    } else if (si && sj) {
+      v = 0.5 * (s_hc[kd] - s_hc[ksum]);
+    } else if (!si && !sj) {
+      v = 0.5 * (s_hc[kd] + s_hc[ksum]);
+    } else {
+      // sin(ks a) cos(kc a) = 0.5 * (sin((ks+kc) a) + sin((ks-kc) a))
+      const int ks = si ? ki : kj, kc = si ? kj : ki;
+      const double sd = ks >= kc ? s_hs[ks - kc] : -s_hs[kc - ks];
+      v = 0.5 * (s_hs[ksum] + sd);
+    }
+    s_g[i * kGStride + j] = v;
+  }
+  __syncthreads();
+
+  // LU with partial pivoting (row interchanges), in place
+  for (int k = 0; k < M; ++k) {
+    if (tid < 32) {
+      double best = -1.0;
+      int best_i = k;
+      for (int i = k + tid; i < M; i += 32) {
+        const double v = fabs(s_g[i * kGStride + k]);
+        if (v > best || (v != v && best == best)) {  // NaN wins, like a propagating max
+          best = v;
+          best_i = i;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        const bool take = (ov > best) || (ov == best && oi < best_i) || (ov != ov && best == best);
+        if (take) {
+          best = ov;
+          best_i = oi;
+        }
+      }
+      if (tid == 0) {
+        s_piv = best_i;
+        s_perm[k] = best_i;
+        if (best == 0.0) s_singular = 1;
+      }
+    }
+    __syncthreads();
+    const int piv = s_piv;
+    if (piv != k) {
+      for (int j = tid; j < M; j += kSolveThreads) {
+        const double t = s_g[k * kGStride + j];
+        s_g[k * kGStride + j] = s_g[piv * kGStride + j];
+        s_g[piv * kGStride + j] = t;
+      }
+    }
+    __syncthreads();
+    const double inv_p = 1.0 / s_g[k * kGStride + k];
+    for (int i = k + 1 + tid; i < M; i += kSolveThreads) s_g[i * kGStride + k] *= inv_p;
+    __syncthreads();
+    const int rem = M - k - 1;
+    for (int e = tid; e < rem * rem; e += kSolveThreads) {
+      const int i = k + 1 + e / rem, j = k + 1 + e % rem;
+      s_g[i * kGStride + j] =
+          fma(-s_g[i * kGStride + k], s_g[k * kGStride + j], s_g[i * kGStride + j]);
+    }
+    __syncthreads();
+  }
+
+  // per-channel solve; channels in chunks of kSolveThreads
+  const double tri = 0.5 * double(M) * double(M + 1);
+  double local = 0.0;
+  for (int64_t c0 = 0; c0 < sh.n_chans; c0 += kSolveThreads) {
+    const int64_t ch = c0 + tid;
+    const bool live = ch < sh.n_chans;
+    if (live) {
+      const double* bp = ws + cand * sh.b_stride_period + ch;
+      for (int m = 0; m < M; ++m) {
+        double v = 0.0;
+        for (int sp = 0; sp < 2 * sh.n_splits; ++sp)
+          v += bp[sp * sh.b_stride_split + int64_t(m) * sh.n_chans];
+        s_b[m * kSolveThreads + tid] = v;
+        s_x[m * kSolveThreads + tid] = v;
+      }
+      // apply the row interchanges, then L (unit lower) and U
+      for (int k = 0; k < M; ++k) {
+        const int p = s_perm[k];
+        if (p != k) {
+          const double t = s_x[k * kSolveThreads + tid];
+          s_x[k * kSolveThreads + tid] = s_x[p * kSolveThreads + tid];
+          s_x[p * kSolveThreads + tid] = t;
+        }
+      }
+      for (int i = 1; i < M; ++i) {
+        double v = s_x[i * kSolveThreads + tid];
+        for (int j = 0; j < i; ++j) v = fma(-s_g[i * kGStride + j], s_x[j * kSolveThreads + tid], v);
+        s_x[i * kSolveThreads + tid] = v;
+      }
+      for (int i = M - 1; i >= 0; --i) {
+        double v = s_x[i * kSolveThreads + tid];
+        for (int j = i + 1; j < M; ++j)
+          v = fma(-s_g[i * kGStride + j], s_x[j * kSolveThreads + tid], v);
+        s_x[i * kSolveThreads + tid] = v / s_g[i * kGStride + i];
+      }
+      double explained = 0.0, penalty = 0.0;
+      for (int m = 0; m < M; ++m) {
+        const double beta = s_x[m * kSolveThreads + tid];
+        explained = fma(beta, s_b[m * kSolveThreads + tid], explained);
+        penalty = fma((lambda * double(m + 1)) / tri, beta * beta, penalty);
+      }
+      local += (sumsq[ch] - explained) / double(sh.n_indices) + penalty;
+    }
+  }
+  local = warp_sum(local);
+  if ((tid & 31) == 0) s_part[tid >> 5] = local;
+  __syncthreads();
+  if (tid == 0) {
+    double total = 0.0;
+    for (int i = 0; i < kSolveThreads / 32; ++i) total += s_part[i];
+    total /= double(n_chans_divisor);
+    fit_error[cand] = s_singular ? __longlong_as_double(0x7ff0000000000000LL) : total;
+  }
+}
+
+// first index of the smallest non-NaN value
+__global__ void __launch_bounds__(1024)
+argmin_kernel(const double* __restrict__ v, int64_t n, double* min_value, int64_t* min_index) {
+  __shared__ double s_v[32];
+  __shared__ int64_t s_i[32];
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  double best = inf;
+  int64_t best_i = INT64_MAX;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) {
+    const double x = v[i];
+    if (x < best || (x == best && i < best_i)) {
+      best = x;
+      best_i = i;
+    }
+  }
+  auto combine = [&](double ov, int64_t oi) {
+    if (ov < best || (ov == best && oi < best_i)) {
+      best = ov;
+      best_i = oi;
+    }
+  };
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int64_t oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    combine(ov, oi);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_v[threadIdx.x >> 5] = best;
+    s_i[threadIdx.x >> 5] = best_i;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    best = s_v[0];
+    best_i = s_i[0];
+    for (int w = 1; w < 32; ++w) combine(s_v[w], s_i[w]);
+    *min_value = best;
+    *min_index = best_i == INT64_MAX ? 0 : best_i;
+  }
+}
+
+static int make_shape(int64_t n_chans, int64_t n_indices, int64_t n_periods, int bandwidth,
+                      int64_t ld_y, EvalShape* sh) {
+  sh->n_chans = n_chans;
+  sh->n_indices = n_indices;
+  sh->n_periods = n_periods;
+  sh->bandwidth = bandwidth;
+  sh->n_rows = 2 * bandwidth + 1;
+  sh->n_chan_tiles = int(ceil_div(n_chans, kChanTile));
+  // enough CTAs for ~4 per SM; a split is at least one sincos batch
+  const int64_t want = ceil_div(int64_t(4) * kNumSMs, n_periods * sh->n_chan_tiles);
+  const int64_t max_splits = ceil_div(n_indices, kSuper);
+  int64_t n_splits = max64(1, min(want, max_splits));
+  sh->split_len = ceil_div(ceil_div(n_indices, n_splits), kSuper) * kSuper;
+  sh->n_splits = int(ceil_div(n_indices, sh->split_len));
+  sh->ld_y = ld_y;
+  sh->b_stride_split = int64_t(sh->n_rows) * n_chans;
+  sh->b_stride_period = 2 * sh->n_splits * sh->b_stride_split;
+  sh->t_stride_split = 4 * int64_t(bandwidth);
+  sh->t_stride_period = sh->n_splits * sh->t_stride_split;
+  sh->t_offset = n_periods * sh->b_stride_period;
+  return PARRM_OK;
+}
+
+}  // namespace parrm
+
+extern "C" {
+
+size_t parrm_eval_workspace_bytes(int64_t n_chans, int64_t n_indices, int64_t n_periods,
+                                  int bandwidth) {
+  if (n_chans <= 0 || n_indices <= 0 || n_periods <= 0 || bandwidth < 0) return 0;
+  parrm::EvalShape sh;
+  parrm::make_shape(n_chans, n_indices, n_periods, bandwidth, n_chans, &sh);
+  return size_t(sh.t_offset + n_periods * sh.t_stride_period + 2) * sizeof(double);
+}
+
+int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
+                       const int64_t* d_indices, int64_t n_chans, int64_t n_indices,
+                       const double* d_periods, int64_t n_periods, int bandwidth, double lambda,
+                       int64_t n_chans_divisor, double* d_fit_error, void* d_workspace,
+                       size_t workspace_bytes, void* stream) {
+  using namespace parrm;
+  PARRM_REQUIRE(n_chans > 0 && n_indices > 0 && n_periods >= 0 && ld_y >= n_chans,
+                "parrm_eval_periods: bad shape");
+  PARRM_REQUIRE(n_chans_divisor > 0, "parrm_eval_periods: n_chans_divisor must be > 0");
+  if (bandwidth < 0 || bandwidth > PARRM_MAX_BANDWIDTH) {
+    set_error("parrm_eval_periods: bandwidth %d outside [0, %d]", bandwidth, PARRM_MAX_BANDWIDTH);
+    return PARRM_ERR_UNSUPPORTED;
+  }
+  if (n_periods == 0) return PARRM_OK;
+  PARRM_REQUIRE(d_y && d_sumsq && d_indices && d_periods && d_fit_error && d_workspace,
+                "parrm_eval_periods: null pointer");
+  PARRM_REQUIRE((reinterpret_cast<uintptr_t>(d_workspace) & 15) == 0,
+                "parrm_eval_periods: workspace must be 16-byte aligned");
+  if (workspace_bytes < parrm_eval_workspace_bytes(n_chans, n_indices, n_periods, bandwidth)) {
+    set_error("parrm_eval_periods: workspace too small");
+    return PARRM_ERR_WORKSPACE;
+  }
+  EvalShape sh;
+  make_shape(n_chans, n_indices, n_periods, bandwidth, ld_y, &sh);
+  PARRM_REQUIRE(sh.n_splits <= 65535 && sh.n_chan_tiles <= 65535,
+                "parrm_eval_periods: grid too large");
+  cudaStream_t s = as_stream(stream);
+  double* ws = static_cast<double*>(d_workspace);
+  dim3 grid((unsigned)n_periods, (unsigned)sh.n_splits, (unsigned)sh.n_chan_tiles);
+  const size_t smem =
+      size_t(kSuper * 16 + (kKT * kRowsPad + kKT * kChanTile + 8 * 2 * kHMax) * sizeof(double));
+  PARRM_CUDA_OK(cudaFuncSetAttribute(eval_accumulate_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  eval_accumulate_kernel<<<grid, kAccThreads, smem, s>>>(d_y, d_indices, d_periods, ws, sh);
+  PARRM_LAUNCH_OK("eval_accumulate_kernel");
+  const size_t solve_smem =
+      size_t(kMaxRows * (kGStride + 2 + 2 * kSolveThreads)) * sizeof(double);
+  PARRM_CUDA_OK(cudaFuncSetAttribute(eval_solve_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     int(solve_smem)));
+  eval_solve_kernel<<<(unsigned)n_periods, kSolveThreads, solve_smem, s>>>(
+      ws, d_sumsq, lambda, n_chans_divisor, d_fit_error, sh);
+  PARRM_LAUNCH_OK("eval_solve_kernel");
+  return PARRM_OK;
+}
+
+int parrm_argmin(const double* d_values, int64_t n, double* d_min_value, int64_t* d_min_index,
+                 void* stream) {
+  PARRM_REQUIRE(n > 0 && d_values && d_min_value && d_min_index, "parrm_argmin: bad arguments");
+  parrm::argmin_kernel<<<1, 1024, 0, parrm::as_stream(stream)>>>(d_values, n, d_min_value,
+                                                                 d_min_index);
+  PARRM_LAUNCH_OK("argmin_kernel");
+  return PARRM_OK;
+}
+
+}  // extern "C"

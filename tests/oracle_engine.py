@@ -1,0 +1,52 @@
+"""Stand-in for ``pyparrm_b200._engine.DeviceEngine`` backed by the CPU oracle.
+
+TEST INFRASTRUCTURE.  It lets the host logic of ``pyparrm_b200.PARRM`` (validation, index
+selection, grids, ranking, lock-step Nelder-Mead, candidate sharding) run under
+``pytest -m "not gpu"`` in a container without a GPU.  The product never imports it.
+"""
+
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from oracle import parrm_oracle as oracle
+
+
+@dataclass
+class OracleTile:
+    z: np.ndarray
+    indices: np.ndarray
+    n_indices: int
+    n_chans: int
+
+
+class OracleEngine:
+    def __init__(self):
+        self.evaluations = 0
+        self.rounds = 0
+
+    def prepare_tiles(self, data, index_sets, outlier_boundary):
+        z = oracle.standardise(data, outlier_boundary)
+        return [OracleTile(z, np.asarray(idx), len(idx), z.shape[0]) for idx in index_sets]
+
+    def tile_from_standardised(self, z, indices):
+        return OracleTile(np.asarray(z), np.asarray(indices), len(indices), z.shape[0])
+
+    def standardise_full(self, data, outlier_boundary):
+        return oracle.standardise(data, outlier_boundary)
+
+    def evaluate(self, tile, periods, bandwidth, lambda_, n_chans_divisor):
+        periods = np.asarray(periods, dtype=np.float64).ravel()
+        self.evaluations += len(periods)
+        self.rounds += 1
+        return oracle.objective_many(
+            periods, tile.z, tile.indices, bandwidth, lambda_, n_chans_divisor,
+            n_jobs=min(8, os.cpu_count() or 1),
+        ).astype(np.float64)
+
+    def build_taps(self, period, phw, hw, omit, direction):
+        return oracle.tap_offsets(period, phw, hw, omit, direction)
+
+    def filter_host(self, data, taps, precision="fp64"):
+        return oracle.apply_filter_direct(np.asarray(data, dtype=np.float64), taps)

@@ -1,0 +1,60 @@
+"""The C-ABI library loads on a CPU-only host and exports what include/parrm_b200.h declares."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from pyparrm_b200 import _native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "parrm_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(parrm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    names = declared_symbols()
+    assert len(names) >= 15
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _native.SIGNATURES, f"{name} has no ctypes signature in _native.py"
+    assert set(_native.SIGNATURES) == set(names)
+
+
+def test_versions_and_constants_agree_with_header():
+    text = open(HEADER).read()
+    assert int(re.search(r"#define PARRM_B200_ABI_VERSION (\d+)", text).group(1)) == _native.ABI_VERSION
+    assert int(re.search(r"#define PARRM_MAX_BANDWIDTH (\d+)", text).group(1)) == _native.MAX_BANDWIDTH
+    assert _native.lib.parrm_abi_version() == _native.ABI_VERSION
+
+
+def test_argument_errors_are_reported_not_crashed():
+    status = _native.lib.parrm_build_taps(-1.0, 0.1, 10, 0, 0, None, None, None)
+    assert status == 1 and "period" in _native.last_error()
+    taps = np.array([3, 2, 1], dtype=np.int32)
+    plan = np.zeros(64, dtype=np.uint8)
+    status = _native.lib.parrm_filter_plan(taps.ctypes.data, 3, 0, plan.ctypes.data, 64)
+    assert status == 1 and "ascending" in _native.last_error()
+    assert _native.lib.parrm_filter_plan_bytes(160) >= 32 + 160 * 4
+
+
+def test_no_silent_cpu_path():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from pyparrm_b200 import PARRM, _engine
+
+    _engine.set_engine(None)
+    p = PARRM(np.random.default_rng(0).standard_normal((1, 200)), 20, 10, verbose=False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        p.find_period()
+    assert _native.device_count() == 0
