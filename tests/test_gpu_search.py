@@ -1,0 +1,168 @@
+"""CUDA period search (standardise, candidate evaluator, whole find_period) vs the reference.
+
+Golden values come from the unmodified reference (tests/golden, oracle/make_golden.py).
+Tolerance: relative error <= 1e-9 on every well-conditioned objective value and on the period
+(BASELINE.json north_star).  Candidates whose Gram matrix the reference itself finds singular
+or hopeless (objective inf or > 1e3; e.g. period exactly 4/3 samples on the bundled
+recording) must come out non-finite or huge here too, never small.
+"""
+
+import numpy as np
+import pytest
+
+from oracle import parrm_oracle as oracle
+from pyparrm_b200 import PARRM, get_example_data_paths
+from pyparrm_b200.synthetic import make_recording
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+HUGE = 1e3
+
+
+def compare_objective(got, want, label=""):
+    want = np.asarray(want, dtype=np.float64)
+    good = np.isfinite(want) & (want < HUGE)
+    rel = np.abs(got[good] - want[good]) / np.abs(want[good])
+    assert rel.size == 0 or rel.max() <= RTOL, f"{label}: max rel err {rel.max():.3e}"
+    bad = ~good
+    assert np.all(~np.isfinite(got[bad]) | (got[bad] > HUGE)), f"{label}: degenerate candidates"
+    return float(rel.max()) if rel.size else 0.0
+
+
+def test_standardise(gpu_engine):
+    import torch
+
+    for dtype, tol in ((np.float64, 1e-13), (np.float32, 2e-6)):
+        x = make_recording(5, 70_001, 2000, 130, seed=21).astype(dtype)
+        x[3] *= 1e-3
+        z = oracle.standardise(x, 3.0)
+        idx_sets = [np.arange(100, 5101), np.unique(np.random.default_rng(0).integers(0, 69_000, 20_000)) + 500]
+        tiles = gpu_engine.prepare_tiles(x, idx_sets, 3.0)
+        for tile, idx in zip(tiles, idx_sets):
+            y = tile.y.cpu().numpy()
+            assert y.shape == (idx.shape[0], 5)
+            assert np.abs(y - z[:, idx].T).max() <= tol * 3.0
+            assert np.allclose(tile.sumsq.cpu().numpy(), (z[:, idx].astype(np.float64) ** 2).sum(1), rtol=max(tol, 1e-12) * 10)
+        full = gpu_engine.standardise_full(x, 3.0)
+        assert full.dtype == dtype and full.shape == z.shape
+        assert np.abs(full - z).max() <= tol * 3.0
+
+
+def test_objective_golden_cases(golden, gpu_engine):
+    g = golden("objective")
+    n, fs, fa = (int(v) for v in g["recording"])
+    worst = 0.0
+    for case in range(int(g["n_cases"])):
+        n_chans, bw, lam, seed = g[f"case{case}_params"]
+        data = make_recording(int(n_chans), n, fs, fa, seed=int(seed))
+        idx = g[f"case{case}_indices"]
+        (tile,) = gpu_engine.prepare_tiles(data, [idx], 3.0)
+        got = gpu_engine.evaluate(tile, g[f"case{case}_periods"], int(bw), float(lam), int(n_chans))
+        worst = max(worst, compare_objective(got, g[f"case{case}_values"], f"case {case}"))
+    print(f"objective golden: worst relative error {worst:.3e}")
+
+
+@pytest.mark.parametrize("name", ["example_dbs", "synthetic_2x30000", "ecog_lfp"])
+def test_every_recorded_evaluation(golden, gpu_engine, name):
+    """All ~1 750 objective evaluations the reference made during find_period, stage by stage."""
+    g = golden(name)
+    if name == "example_dbs":
+        data = np.load(get_example_data_paths("example_data"))
+    elif name == "ecog_lfp":
+        data = np.load(get_example_data_paths("ecog_lfp_data"))
+    else:
+        n_chans, n, fs, fa, seed = (int(v) for v in g["recording"])
+        data = make_recording(n_chans, n, fs, fa, seed=seed)
+    idx_sets = [g[f"run{r}_indices"] for r in range(int(g["n_runs"]))]
+    tiles = gpu_engine.prepare_tiles(data, idx_sets, 3.0)
+    calls = g["calls"]
+    by_len = {len(i): t for i, t in zip(idx_sets, tiles)}
+    worst = 0.0
+    stages = sorted({(int(b), float(l), int(n)) for _, b, l, n, _ in calls})
+    for bw, lam, n_idx in stages:
+        rows = calls[(calls[:, 1] == bw) & (calls[:, 2] == lam) & (calls[:, 3] == n_idx)]
+        got = gpu_engine.evaluate(by_len[n_idx], rows[:, 0], bw, lam, data.shape[0])
+        worst = max(worst, compare_objective(got, rows[:, 4], f"{name} bw={bw} lambda={lam}"))
+    print(f"{name}: {len(calls)} evaluations, worst relative error {worst:.3e}")
+
+
+def test_batch_split_and_single_candidate_agree(gpu_engine):
+    """Few candidates (sample-split CTAs) and many candidates (one CTA each) give the same value."""
+    data = make_recording(3, 60_000, 2000, 130, seed=12)
+    idx = np.arange(10_000, 35_001)
+    (tile,) = gpu_engine.prepare_tiles(data, [idx], 3.0)
+    periods = 2000 / 130 * (1 + np.linspace(-1e-3, 1e-3, 700))
+    many = gpu_engine.evaluate(tile, periods, 20, 1.0, 3)
+    for k in (0, 123, 699):
+        one = gpu_engine.evaluate(tile, periods[k : k + 1], 20, 1.0, 3)
+        assert abs(one[0] - many[k]) <= 1e-12 * abs(many[k])
+    val, pos = gpu_engine.argmin(gpu_engine.evaluate_device(tile, periods, 20, 1.0, 3))
+    assert pos == int(np.argmin(many)) and val == many.min()
+
+
+def test_wide_and_narrow_channel_counts(gpu_engine):
+    """1, 64 (one full channel tile), 65 and 130 channels against the oracle."""
+    base = make_recording(130, 12_000, 2000, 130, seed=13)
+    idx = np.arange(1000, 6001)
+    periods = 2000 / 130 * (1 + np.array([-2e-3, 0.0, 3e-6, 1e-3]))
+    for n_chans in (1, 64, 65, 130):
+        data = np.ascontiguousarray(base[:n_chans])
+        (tile,) = gpu_engine.prepare_tiles(data, [idx], 3.0)
+        got = gpu_engine.evaluate(tile, periods, 10, 1.0, n_chans)
+        z = oracle.standardise(data, 3.0)
+        want = oracle.objective_many(periods, z, idx, 10, 1.0, n_chans, n_jobs=8)
+        compare_objective(got, want, f"{n_chans} channels")
+
+
+@pytest.mark.parametrize("name", ["example_dbs", "synthetic_2x30000", "ecog_lfp"])
+def test_find_period_matches_reference(golden, gpu_engine, name):
+    g = golden(name)
+    if name == "example_dbs":
+        parrm = PARRM(np.load(get_example_data_paths("example_data")), 200, 150, verbose=False)
+        parrm.find_period()
+    elif name == "ecog_lfp":
+        parrm = PARRM(np.load(get_example_data_paths("ecog_lfp_data")), 1000, 130, verbose=False)
+        parrm.find_period(random_seed=0)
+    else:
+        n_chans, n, fs, fa, seed = (int(v) for v in g["recording"])
+        parrm = PARRM(make_recording(n_chans, n, fs, fa, seed=seed), fs, fa, verbose=False)
+        parrm.find_period(random_seed=0)
+    want = float(g["period"])
+    print(f"{name}: period {parrm.period!r} reference {want!r}")
+    assert isinstance(parrm.period, np.float64)
+    assert abs(parrm.period - want) <= RTOL * want
+
+
+def test_whole_workflow_known_answer(golden, gpu_engine):
+    """examples/plot_use_parrm.py end to end: period, filter, np.allclose(matlab_filtered)."""
+    g = golden("example_dbs")
+    data = np.load(get_example_data_paths("example_data"))
+    parrm = PARRM(data=data, sampling_freq=200, artefact_freq=150, verbose=False)
+    parrm.find_period()
+    parrm.create_filter(filter_half_width=2000, omit_n_samples=20, filter_direction="both",
+                        period_half_width=0.01)
+    out = parrm.filter_data()
+    assert np.array_equal(np.flatnonzero(parrm.filter < 0) - 2000, g["taps"])
+    assert np.allclose(out, g["matlab_filtered"])
+    assert np.abs(out - g["filtered"]).max() <= RTOL * np.abs(data).max()
+
+
+@pytest.mark.parametrize("n_chans", [1, 2])
+@pytest.mark.parametrize("n_samples", [100, 300, 25000])
+@pytest.mark.parametrize("search_portion", [None, 0.5])
+def test_reference_suite_matrix(gpu_engine, n_chans, n_samples, search_portion):
+    """The reference's own smoke matrix (tests/test_parrm.py:17-68) incl. degenerate period 2.0."""
+    rng = np.random.default_rng(44)
+    data = rng.standard_normal((n_chans, n_samples))
+    parrm = PARRM(data=data, sampling_freq=20, artefact_freq=10, verbose=False)
+    search = None if search_portion is None else np.arange(0, n_samples * search_portion)
+    parrm.find_period(search_samples=search, assumed_periods=20 / 10, random_seed=44, n_jobs=2)
+    for direction in ["future", "past", "both"]:
+        parrm.create_filter(filter_direction=direction)
+    filtered = parrm.filter_data()
+    assert filtered.shape == data.shape and isinstance(filtered, np.ndarray)
+    other = rng.standard_normal((1, 50))
+    assert parrm.filter_data(other).shape == other.shape
+    assert repr(parrm) == (
+        f"PARRM object | Data: ({n_chans} channels x {n_samples} times) | Period: {parrm.period :.4f}")
+    assert np.isfinite(parrm.period)
