@@ -11,7 +11,9 @@
 //     channel) and, by the product-to-sum identities, is a linear function of the 4*bw+1
 //     harmonic sums  C_m = sum_i cos(m a_i),  S_m = sum_i sin(m a_i),  m = 0..2*bw;
 //   * the right-hand sides are one small GEMM  B = W' Y  (M x C, K = N);
-//   * with beta solving the normal equations,  sum_i (y - W beta)_i^2 = y'y - beta' W'y.
+//   * the residual sum of squares is the quadratic form  y'y - 2 beta'(W'y) + beta'(W'W) beta,
+//     exact for any beta (so, like the reference's explicit residual, insensitive to first
+//     order to rounding in the solve).
 // Kernel 1 (accumulate) walks the samples: one accurate sincos(a_i) per sample, harmonics by
 // the angle-addition recurrence in registers, harmonic sums in registers, and a register-tiled
 // FP64 FMA GEMM from shared-memory tiles for B.  Samples can be split over several CTAs per
@@ -232,7 +234,8 @@ eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sums
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int M = sh.n_rows, bw = sh.bandwidth, two_bw = 2 * bw;
   double* s_g = reinterpret_cast<double*>(smem_raw);   // [M][kGStride] LU factors
-  double* s_hc = s_g + kMaxRows * kGStride;   // C_0..C_2bw
+  double* s_g0 = s_g + kMaxRows * kGStride;   // [M][kGStride] Gram matrix, kept unfactored
+  double* s_hc = s_g0 + kMaxRows * kGStride;  // C_0..C_2bw
   double* s_hs = s_hc + kMaxRows;             // S_0..S_2bw
   double* s_b = s_hs + kMaxRows;              // [M][kSolveThreads] right-hand sides
   double* s_x = s_b + kMaxRows * kSolveThreads;  // [M][kSolveThreads] work / solution
@@ -284,6 +287,7 @@ eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sums
       v = 0.5 * (s_hs[ksum] + sd);
     }
     s_g[i * kGStride + j] = v;
+    s_g0[i * kGStride + j] = v;
   }
   __syncthreads();
 
@@ -372,13 +376,19 @@ eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sums
           v = fma(-s_g[i * kGStride + j], s_x[j * kSolveThreads + tid], v);
         s_x[i * kSolveThreads + tid] = v / s_g[i * kGStride + i];
       }
-      double explained = 0.0, penalty = 0.0;
+      // sum_i (y - W beta)^2 = y'y - 2 beta'b + beta'G beta holds for ANY beta, so like the
+      // reference's explicit residual (parrm.py:630) it is only second-order sensitive to the
+      // rounding of the solve; y'y - beta'b would be first-order sensitive.
+      double cross = 0.0, quad = 0.0, penalty = 0.0;
       for (int m = 0; m < M; ++m) {
         const double beta = s_x[m * kSolveThreads + tid];
-        explained = fma(beta, s_b[m * kSolveThreads + tid], explained);
+        double gb = 0.0;
+        for (int j = 0; j < M; ++j) gb = fma(s_g0[m * kGStride + j], s_x[j * kSolveThreads + tid], gb);
+        cross = fma(beta, s_b[m * kSolveThreads + tid], cross);
+        quad = fma(beta, gb, quad);
         penalty = fma((lambda * double(m + 1)) / tri, beta * beta, penalty);
       }
-      local += (sumsq[ch] - explained) / double(sh.n_indices) + penalty;
+      local += ((sumsq[ch] - 2.0 * cross) + quad) / double(sh.n_indices) + penalty;
     }
   }
   local = warp_sum(local);
@@ -504,7 +514,7 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
   eval_accumulate_kernel<<<grid, kAccThreads, smem, s>>>(d_y, d_indices, d_periods, ws, sh);
   PARRM_LAUNCH_OK("eval_accumulate_kernel");
   const size_t solve_smem =
-      size_t(kMaxRows * (kGStride + 2 + 2 * kSolveThreads)) * sizeof(double);
+      size_t(kMaxRows * (2 * kGStride + 2 + 2 * kSolveThreads)) * sizeof(double);
   PARRM_CUDA_OK(cudaFuncSetAttribute(eval_solve_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      int(solve_smem)));
