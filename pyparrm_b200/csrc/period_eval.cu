@@ -31,6 +31,9 @@ constexpr int kGroups = 4;        // harmonic groups per sample (kGroups * kKT =
 constexpr int kHMax = (2 * PARRM_MAX_BANDWIDTH + kGroups - 1) / kGroups;  // 12
 constexpr int kMaxRows = 2 * PARRM_MAX_BANDWIDTH + 1;                     // 47
 constexpr int kRowsPad = 48;      // padded design-matrix row: 8 row groups x 6
+constexpr int kRowStride = 50;    // smem stride of a sample's row (doubles): 16-byte aligned
+                                  // for LDS.128 and 100 words = 4 banks/lane, so the per-sample
+                                  // stores of the generator are 2-way instead of 32-way conflicted
 constexpr int kRowTile = 6;
 static_assert(kMaxRows <= kRowsPad, "row groups must cover the widest design matrix");
 constexpr int kColTile = 4;
@@ -76,8 +79,8 @@ eval_accumulate_kernel(const double* __restrict__ y, const int64_t* __restrict__
                        const EvalShape sh) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* s_cs = reinterpret_cast<double2*>(smem_raw);                 // [kSuper] (cos, sin)
-  double* s_w = reinterpret_cast<double*>(smem_raw + kSuper * 16);      // [kKT][kRowsPad]
-  double* s_y = s_w + kKT * kRowsPad;                                   // [kKT][kChanTile]
+  double* s_w = reinterpret_cast<double*>(smem_raw + kSuper * 16);      // [kKT][kRowStride]
+  double* s_y = s_w + kKT * kRowStride;                                  // [kKT][kChanTile]
   double* s_red = s_y + kKT * kChanTile;                                // [8 warps][2*H]
   constexpr int H = kHMax;
 
@@ -133,7 +136,7 @@ eval_accumulate_kernel(const double* __restrict__ y, const int64_t* __restrict__
         const double2 cs1 = s_cs[sub * kKT + gi];
         double c, s;
         cpow(cs1.x, cs1.y, m0, c, s);
-        double* wrow = s_w + gi * kRowsPad;
+        double* wrow = s_w + gi * kRowStride;
         if (gg == 0) wrow[0] = live ? 1.0 : 0.0;
 #pragma unroll
         for (int j = 0; j < H; ++j) {
@@ -162,13 +165,13 @@ eval_accumulate_kernel(const double* __restrict__ y, const int64_t* __restrict__
       __syncthreads();
       // ---- B += W' Y over this K-half's 32 samples ----
       if (rows_live) {
-        const double* wp = s_w + (kh * (kKT / 2)) * kRowsPad + rg * kRowTile;
+        const double* wp = s_w + (kh * (kKT / 2)) * kRowStride + rg * kRowTile;
         const double* yp = s_y + (kh * (kKT / 2)) * kChanTile + cg * kColTile;
 #pragma unroll 4
         for (int k = 0; k < kKT / 2; ++k) {
-          const double2 w01 = *reinterpret_cast<const double2*>(wp + k * kRowsPad);
-          const double2 w23 = *reinterpret_cast<const double2*>(wp + k * kRowsPad + 2);
-          const double2 w45 = *reinterpret_cast<const double2*>(wp + k * kRowsPad + 4);
+          const double2 w01 = *reinterpret_cast<const double2*>(wp + k * kRowStride);
+          const double2 w23 = *reinterpret_cast<const double2*>(wp + k * kRowStride + 2);
+          const double2 w45 = *reinterpret_cast<const double2*>(wp + k * kRowStride + 4);
           const double2 y01 = *reinterpret_cast<const double2*>(yp + k * kChanTile);
           const double2 y23 = *reinterpret_cast<const double2*>(yp + k * kChanTile + 2);
           const double wv[kRowTile] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y};
@@ -508,7 +511,7 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
   double* ws = static_cast<double*>(d_workspace);
   dim3 grid((unsigned)n_periods, (unsigned)sh.n_splits, (unsigned)sh.n_chan_tiles);
   const size_t smem =
-      size_t(kSuper * 16 + (kKT * kRowsPad + kKT * kChanTile + 8 * 2 * kHMax) * sizeof(double));
+      size_t(kSuper * 16 + (kKT * kRowStride + kKT * kChanTile + 8 * 2 * kHMax) * sizeof(double));
   PARRM_CUDA_OK(cudaFuncSetAttribute(eval_accumulate_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   eval_accumulate_kernel<<<grid, kAccThreads, smem, s>>>(d_y, d_indices, d_periods, ws, sh);

