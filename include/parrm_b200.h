@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PARRM_B200_ABI_VERSION 1
+#define PARRM_B200_ABI_VERSION 2
 
 typedef enum {
   PARRM_OK = 0,
@@ -46,6 +46,13 @@ typedef enum { PARRM_F64 = 0, PARRM_F32 = 1 } parrm_dtype_t;
 
 /* filter_direction strings of PARRM.create_filter (parrm.py:710-714, 817-820) */
 typedef enum { PARRM_DIR_BOTH = 0, PARRM_DIR_PAST = 1, PARRM_DIR_FUTURE = 2 } parrm_direction_t;
+
+/* how parrm_filter_plan() may re-associate the tap sum (the result is the same tap set) */
+typedef enum {
+  PARRM_PLAN_AUTO = 0,    /* comb boxes when the tap set has progressions, else plain gather */
+  PARRM_PLAN_GATHER = 1,  /* one load per tap */
+  PARRM_PLAN_COMB = 2     /* comb boxes; PARRM_ERR_UNSUPPORTED if the tap set has none */
+} parrm_plan_strategy_t;
 
 #define PARRM_MAX_BANDWIDTH 23  /* harmonics per candidate; the reference uses 5/10/20 (parrm.py:295) */
 
@@ -134,10 +141,20 @@ int parrm_build_taps(double period, double period_half_width, int64_t filter_hal
  * parrm_filter_plan() builds on the host from the ascending tap offsets (as produced by
  * parrm_build_taps) and that the caller uploads verbatim; parrm_filter_apply() takes both
  * the host copy (launch geometry) and the device copy (read by the kernels).
+ *
+ * Every tap has the same weight (parrm.py:829), so the planner may regroup the tap set into
+ * windowed stride-d sums ("comb boxes") plus single taps -- an exact identity over which
+ * offsets are summed, pyparrm_b200/csrc/filter_plan.h -- which the strip kernel evaluates with
+ * ~10x fewer shared-memory loads than one load per tap.  parrm_filter_plan_info() exposes the
+ * decomposition (tests expand it back into the tap set).
  * ---------------------------------------------------------------------- */
 size_t parrm_filter_plan_bytes(int32_t n_taps);
-int parrm_filter_plan(const int32_t* h_taps, int32_t n_taps, int dtype,
+int parrm_filter_plan(const int32_t* h_taps, int32_t n_taps, int dtype, int strategy,
                       void* h_plan, size_t plan_bytes);
+/* info[0..15] = kind, stride, n_kinds, window0, window1, n_box0, n_box1, n_plus, n_minus,
+ * centre, cost_milli, n_taps, w_min, w_max, n_terms, 0;  terms (capacity >= n_terms, may be
+ * NULL) = box offsets of length 0, of length 1, +1 taps, -1 taps. */
+int parrm_filter_plan_info(const void* h_plan, int32_t* info, int32_t* terms, int32_t capacity);
 int parrm_filter_apply(const void* d_x, int64_t ld_x, int64_t x_t0, int64_t n_x,
                        void* d_out, int64_t ld_out, int64_t t0, int64_t n_out,
                        int64_t n_samples_total, int64_t n_chans,

@@ -349,18 +349,21 @@ class DeviceEngine:
             return d_taps[:n].cpu().numpy()
 
     # ------------------------------------------------------------------- filter
-    def _plan(self, taps: np.ndarray, dtype_code: int):
+    def _plan(self, taps: np.ndarray, dtype_code: int, strategy: int | None = None):
         """Host + device copies of the filter plan for a tap list (small LRU cache)."""
         t = self.torch
         taps = np.ascontiguousarray(taps, dtype=np.int32)
-        key = (dtype_code, taps.tobytes())
+        if strategy is None:
+            strategy = int(os.environ.get("PYPARRM_B200_PLAN", _native.PLAN_AUTO))
+        key = (dtype_code, strategy, taps.tobytes())
         hit = self._plans.get(key)
         if hit is not None:
             return hit
         nbytes = lib.parrm_filter_plan_bytes(int(taps.shape[0]))
         h_plan = np.zeros(nbytes, dtype=np.uint8)
         check(lib.parrm_filter_plan(_vp(taps.ctypes.data), int(taps.shape[0]), dtype_code,
-                                    _vp(h_plan.ctypes.data), nbytes), "parrm_filter_plan")
+                                    int(strategy), _vp(h_plan.ctypes.data), nbytes),
+              "parrm_filter_plan")
         d_plan = t.from_numpy(h_plan).to(self.device)
         if len(self._plans) >= 16:
             self._plans.pop(next(iter(self._plans)))
@@ -382,14 +385,14 @@ class DeviceEngine:
             data = np.ascontiguousarray(data)
         return data, code
 
-    def filter_device(self, d_x, taps: np.ndarray, d_out=None, stream=None):
+    def filter_device(self, d_x, taps: np.ndarray, d_out=None, stream=None, strategy=None):
         """Filter a device-resident [C, T] tensor (float64 or float32); returns a device tensor."""
         t = self.torch
         code = {t.float64: _native.F64, t.float32: _native.F32}[d_x.dtype]
         if d_x.dim() != 2 or d_x.stride(1) != 1:
             raise ValueError("device input must be a 2-D row-major tensor")
         n_chans, n_samples = d_x.shape
-        h_plan, d_plan, _ = self._plan(taps, code)
+        h_plan, d_plan, _ = self._plan(taps, code, strategy)
         if d_out is None:
             d_out = t.empty((n_chans, n_samples), dtype=d_x.dtype, device=d_x.device)
         stream = stream or t.cuda.current_stream()
@@ -403,7 +406,8 @@ class DeviceEngine:
             self.launches += 1
         return d_out
 
-    def filter_host(self, data: np.ndarray, taps: np.ndarray, precision: str = "fp64") -> np.ndarray:
+    def filter_host(self, data: np.ndarray, taps: np.ndarray, precision: str = "fp64",
+                    strategy: int | None = None) -> np.ndarray:
         """``filter_data`` body (parrm.py:861-869): NumPy [C, T] in, float64 NumPy [C, T] out."""
         t = self.torch
         data, _ = self._as_float_array(data, allow_f32=False)
@@ -418,7 +422,7 @@ class DeviceEngine:
         compute_f32 = precision == "fp32"
         code = _native.F32 if compute_f32 else _native.F64
         with self._lock, t.cuda.device(self.device):
-            h_plan, d_plan, (w_lo, w_hi) = self._plan(taps, code)
+            h_plan, d_plan, (w_lo, w_hi) = self._plan(taps, code, strategy)
             span = w_hi - w_lo
             row_bytes = n_samples * 8
             # chunk list: (c0, c1, t0, t1, x0, x1) -- channels [c0,c1), outputs [t0,t1), inputs [x0,x1)

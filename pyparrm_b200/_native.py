@@ -19,7 +19,8 @@ F64, F32 = 0, 1
 DIR_BOTH, DIR_PAST, DIR_FUTURE = 0, 1, 2
 DIRECTIONS = {"both": DIR_BOTH, "past": DIR_PAST, "future": DIR_FUTURE}
 MAX_BANDWIDTH = 23
-ABI_VERSION = 1
+ABI_VERSION = 2
+PLAN_AUTO, PLAN_GATHER, PLAN_COMB = 0, 1, 2
 
 # name -> (restype, argtypes); mirrors include/parrm_b200.h one to one
 SIGNATURES = {
@@ -55,7 +56,8 @@ SIGNATURES = {
         c_int, [c_double, c_double, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]
     ),
     "parrm_filter_plan_bytes": (c_size_t, [c_int32]),
-    "parrm_filter_plan": (c_int, [c_void_p, c_int32, c_int, c_void_p, c_size_t]),
+    "parrm_filter_plan": (c_int, [c_void_p, c_int32, c_int, c_int, c_void_p, c_size_t]),
+    "parrm_filter_plan_info": (c_int, [c_void_p, c_void_p, c_void_p, c_int32]),
     "parrm_filter_apply": (
         c_int,
         [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
@@ -100,3 +102,33 @@ def check(status: int, what: str) -> None:
 
 def device_count() -> int:
     return int(lib.parrm_device_count())
+
+
+def plan_filter(taps, dtype: int = F64, strategy: int = PLAN_AUTO):
+    """Build a filter plan on the host; returns ``(plan_bytes, description)``.
+
+    ``description`` is the decomposition the strip kernel evaluates: ``kind`` (0 gather,
+    1 comb), ``stride``, ``windows`` (box lengths), ``boxes`` (one offset array per length),
+    ``plus`` / ``minus`` single taps, ``centre`` and the modelled ``cost`` in loads per output.
+    Pure host work: usable without a GPU.
+    """
+    import numpy as np
+
+    taps = np.ascontiguousarray(taps, dtype=np.int32)
+    nbytes = lib.parrm_filter_plan_bytes(int(taps.shape[0]))
+    plan = np.zeros(nbytes, dtype=np.uint8)
+    check(lib.parrm_filter_plan(taps.ctypes.data, int(taps.shape[0]), dtype, strategy,
+                                plan.ctypes.data, nbytes), "parrm_filter_plan")
+    info = np.zeros(16, dtype=np.int32)
+    terms = np.zeros(256, dtype=np.int32)
+    check(lib.parrm_filter_plan_info(plan.ctypes.data, info.ctypes.data, terms.ctypes.data, 256),
+          "parrm_filter_plan_info")
+    kind, stride, n_kinds, w0, w1, b0, b1, n_plus, n_minus, centre, cost = (int(v) for v in info[:11])
+    cuts = np.cumsum([0, b0, b1, n_plus, n_minus])
+    parts = [terms[cuts[i]:cuts[i + 1]].copy() for i in range(4)]
+    desc = {
+        "kind": kind, "stride": stride, "windows": [w0, w1][:n_kinds],
+        "boxes": parts[:2][:n_kinds], "plus": parts[2], "minus": parts[3],
+        "centre": centre, "cost": cost / 1000.0, "n_taps": int(info[11]),
+    }
+    return plan, desc

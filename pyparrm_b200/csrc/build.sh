@@ -10,11 +10,11 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17
        -Xcompiler -fPIC -I"$root/include" -I"$here" ${PARRM_NVCC_EXTRA:-})
 pids=()
-for src in cabi taps filter standardise period_eval; do
+for src in cabi taps filter filter_plan standardise period_eval; do
   "$NVCC" "${FLAGS[@]}" -c "$here/$src.cu" -o "$obj/$src.o" &
   pids+=($!)
 done
 for pid in "${pids[@]}"; do wait "$pid"; done
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$out" "$obj"/cabi.o "$obj"/taps.o "$obj"/filter.o "$obj"/standardise.o \
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$out" "$obj"/cabi.o "$obj"/taps.o "$obj"/filter.o "$obj"/filter_plan.o "$obj"/standardise.o \
         "$obj"/period_eval.o -cudart static
 echo "built $out"

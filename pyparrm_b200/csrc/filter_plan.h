@@ -1,5 +1,18 @@
 // Relocatable filter plan blob shared by host and device (offsets, no pointers).
 // Built on the host by parrm_filter_plan(), uploaded verbatim by the caller.
+//
+// A plan is an exact integer re-association of the tap set T of PARRM._generate_filter
+// (parrm.py:803-833).  Every tap has the same weight -1/n_taps (parrm.py:829), so
+//
+//     sum_{w in T} x[t - w]  =  sum_b D_{k(b)}[t - a_b]  +  sum_{w in plus} x[t - w]
+//                               -  sum_{w in minus} x[t - w]  +  centre * x[t]
+//
+// with "comb boxes"  D_k[i] = sum_{q=0}^{m_k - 1} x[i - q*d]  of at most two window lengths
+// m_0, m_1 over one common stride d.  The taps of a phase-matched comb sit near the multiples
+// of the period, so for d ~ an integer multiple of the period they fall into a few long
+// arithmetic progressions; a progression of m_k members costs one shared-memory load from the
+// D_k array instead of m_k loads from x.  The identity is over integers (which offsets are
+// summed), so the result differs from the plain gather only by floating-point association.
 #pragma once
 #include <stdint.h>
 
@@ -7,29 +20,36 @@ namespace parrm {
 
 constexpr uint32_t kPlanMagic = 0x4D525250u;  // "PRRM"
 constexpr uint32_t kPlanVersion = 2;
-constexpr int kMaxTerms = 96;                 // structured terms passed as kernel parameters
+constexpr int kMaxTerms = 120;                // structured terms passed as kernel parameters
+constexpr int kMaxBoxKinds = 2;
 
 enum PlanKind : int32_t {
-  kPlanGather = 0,      // y = x[t] - mean of the in-range taps, one shared-memory load per tap
-  kPlanStridePrefix = 1 // taps grouped into arithmetic progressions of one common stride d;
-                        // each progression costs two loads from a stride-d prefix sum
+  kPlanGather = 0,  // one shared-memory load per tap
+  kPlanComb = 1     // comb boxes + single taps (see above)
 };
 
 struct FilterPlanHeader {
   uint32_t magic;
   uint32_t version;
   int32_t n_taps;
-  int32_t w_min, w_max;  // smallest / largest signed tap offset
-  int32_t kind;          // PlanKind
-  int32_t taps_offset;   // byte offset of int32 taps[n_taps]
-  int32_t dtype;         // parrm_dtype_t the plan was built for
-  int32_t stride;        // common difference d of the progressions (kind 1)
-  int32_t n_terms;       // number of (offset, coefficient) terms (kind 1)
-  int32_t off_offset;    // byte offset of int32 term_off[n_terms]
-  int32_t coef_offset;   // byte offset of double term_coef[n_terms]
-  int32_t n_progressions;
-  int32_t reserved[3];
+  int32_t w_min, w_max;   // smallest / largest signed tap offset
+  int32_t kind;           // PlanKind
+  int32_t taps_offset;    // byte offset of int32 taps[n_taps]
+  int32_t dtype;          // parrm_dtype_t the plan was built for
+  // ---- kPlanComb ----
+  int32_t stride;                   // d
+  int32_t n_kinds;                  // 1 or 2 box lengths in use
+  int32_t window[kMaxBoxKinds];     // m_k
+  int32_t n_box[kMaxBoxKinds];      // boxes of each length
+  int32_t a_min[kMaxBoxKinds];      // smallest / largest box offset of each length
+  int32_t a_max[kMaxBoxKinds];
+  int32_t n_plus, n_minus;          // single taps with coefficient +1 / -1
+  int32_t centre;                   // coefficient of x[t] inside the tap sum (0 or negative)
+  int32_t terms_offset;             // byte offset of int32 terms[]: boxes kind 0, boxes kind 1,
+                                    // plus singles, minus singles
+  int32_t cost_milli;               // modelled shared-memory loads per output x 1000
+  int32_t reserved[9];
 };
-static_assert(sizeof(FilterPlanHeader) == 64, "plan header is 64 bytes");
+static_assert(sizeof(FilterPlanHeader) == 128, "plan header is 128 bytes");
 
 }  // namespace parrm

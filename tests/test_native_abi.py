@@ -41,7 +41,7 @@ def test_argument_errors_are_reported_not_crashed():
     assert status == 1 and "period" in _native.last_error()
     taps = np.array([3, 2, 1], dtype=np.int32)
     plan = np.zeros(4096, dtype=np.uint8)
-    status = _native.lib.parrm_filter_plan(taps.ctypes.data, 3, 0, plan.ctypes.data, 4096)
+    status = _native.lib.parrm_filter_plan(taps.ctypes.data, 3, 0, 0, plan.ctypes.data, 4096)
     assert status == 1 and "ascending" in _native.last_error()
     assert _native.lib.parrm_filter_plan_bytes(160) >= 32 + 160 * 4
 
