@@ -228,6 +228,7 @@ struct StripArgs {
   int32_t tab_d0, tab_d1, tab_x;       // int offsets of the three sub-tables
   int32_t tab_stride_d0, tab_stride_d1, tab_stride_x;
   int32_t small_plan;                  // every table row fits the preloaded registers
+  int32_t piece_steps;                 // pipelined kernel: chunks per piece (direct re-evaluation)
   int32_t off[kMaxTerms];              // per-term ring offsets: (-(a - a_lo_k)) mod |D_k| for
                                        // boxes, (-w) mod |X| for single taps
 };
@@ -643,8 +644,381 @@ __global__ void __launch_bounds__(NT) filter_comb_strip_kernel(const StripArgs<T
   }
 }
 
+// ====================================================================================
+// Pipelined strip kernel: the same rings and arithmetic as filter_comb_strip_kernel, but the
+// box slide and the gather run on different warps and overlap.  ND "slide" threads run one
+// chunk ahead: they issue the TMA copies, wait for them, and slide the boxes into chunk n + 1
+// while the NG "gather" threads produce the outputs of chunk n.  The D rings hold one chunk
+// more than the gather reads (X two more), and two mbarrier pairs hand chunks over:
+//     full[n & 1]   slide -> gather   chunk n of every D ring is written
+//     empty[n & 1]  gather -> slide   the gather of chunk n has read everything it needs
+// The latency-bound dependent adds of the slide thus hide behind the bandwidth-bound gather,
+// and a step has no CTA-wide barrier at all.  A piece covers at most `piece_steps` chunks, so
+// the boxes are re-evaluated directly often enough to bound rounding drift.
+// ====================================================================================
+template <typename T, int NG, int ND, int RU>
+__global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripArgs<T> a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem_raw);  // [kMaxPrefetch] TMA chunks
+  uint64_t* const full = bars + kMaxPrefetch;                    // [2]
+  uint64_t* const empty = full + 2;                              // [2]
+  int32_t* const tab = reinterpret_cast<int32_t*>(smem_raw + 128);
+  constexpr int VEC = 16 / sizeof(T);
+  constexpr int ES = int(sizeof(T));
+  constexpr int NT = NG + ND;
+  const int tile = a.tile;
+  const int RX = a.nq_x * tile;
+  T* const sX = reinterpret_cast<T*>(smem_raw + 128 + a.tab_bytes);
+  T* const sD0 = sX + RX + tile;
+  const int RD0 = a.nq_d[0] * tile;
+  T* const sD1 = sD0 + RD0 + tile;
+  const int RD1 = a.nk > 1 ? a.nq_d[1] * tile : 0;
+  const int tid = threadIdx.x;
+  const bool is_gather = tid < NG;
+  const int gt = tid;        // gather thread index (valid when is_gather)
+  const int dt = tid - NG;   // slide thread index (valid otherwise)
+  const int P = a.prefetch;
+  const int Sc = a.steps_per_chan;
+  const int d = a.d;
+  const int64_t lo_valid = max64(0, a.x_t0);
+  const int64_t hi_valid = min64(a.n_total, a.x_t0 + a.n_x);
+  const T inv_n = T(1) / T(a.n_taps);
+  const T centre = T(a.centre);
+  const int n_box0 = a.n_box[0], n_box1 = a.nk > 1 ? a.n_box[1] : 0;
+  const int n_plus = a.n_plus, n_minus = a.n_minus;
+  const int back0 = a.nq_d[0] - 2, back1 = a.nk > 1 ? a.nq_d[1] - 2 : 0;
+
+  if (tid == 0) {
+    for (int b = 0; b < kMaxPrefetch; ++b) mbar_init(&bars[b], 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full[s], 1);         // one elected slide thread arrives
+      mbar_init(&empty[s], NG / 32);  // one lane of every gather warp arrives
+    }
+    fence_mbar_init();
+  }
+  {  // gather address table (see filter_comb_strip_kernel)
+    const int x_base = 128 + a.tab_bytes;
+    const int d0_base = x_base + (RX + tile) * ES;
+    const int d1_base = d0_base + (RD0 + tile) * ES;
+    const int n_x_terms = 1 + n_plus + n_minus;
+    for (int i = tid; i < a.nq_d[0] * n_box0; i += NT) {
+      const int slot = i / n_box0, t = i - slot * n_box0;
+      tab[a.tab_d0 + slot * a.tab_stride_d0 + t] =
+          d0_base + wrap_up(slot * tile + a.off[t], RD0) * ES;
+    }
+    if (a.nk > 1)
+      for (int i = tid; i < a.nq_d[1] * n_box1; i += NT) {
+        const int slot = i / n_box1, t = i - slot * n_box1;
+        tab[a.tab_d1 + slot * a.tab_stride_d1 + t] =
+            d1_base + wrap_up(slot * tile + a.off[n_box0 + t], RD1) * ES;
+      }
+    for (int i = tid; i < a.nq_x * n_x_terms; i += NT) {
+      const int slot = i / n_x_terms, t = i - slot * n_x_terms;
+      const int off = t == 0 ? 0 : a.off[n_box0 + n_box1 + t - 1];
+      tab[a.tab_x + slot * a.tab_stride_x + t] = x_base + wrap_up(slot * tile + off, RX) * ES;
+    }
+  }
+  // phase parities; every thread keeps the ones its role waits on
+  uint32_t tma_phase = 0, tma_bits = 0;  // slide threads
+  uint32_t full_phase = 0;               // gather threads: bit s = parity to wait for
+  uint32_t empty_phase = 0;              // slide threads
+
+  const int64_t F_begin = a.total_steps * int64_t(blockIdx.x) / int64_t(gridDim.x);
+  const int64_t F_end = a.total_steps * int64_t(blockIdx.x + 1) / int64_t(gridDim.x);
+
+  for (int64_t F = F_begin; F < F_end;) {
+    const int64_t chan = F / Sc;
+    const int s0 = int(F - chan * Sc);
+    const int s1 = int(min64(min64(Sc, s0 + (F_end - F)), int64_t(s0) + a.piece_steps));
+    F += s1 - s0;
+
+    const T* xrow = a.x + chan * a.ld_x - a.x_t0;
+    T* orow = a.out + chan * a.ld_out - a.t0;
+    const int gamma =
+        int((VEC - int((reinterpret_cast<uintptr_t>(xrow) / sizeof(T)) % VEC)) % VEC);
+    const int64_t j_first = floor_div(a.t0 - gamma, tile);
+    const int64_t j_last = floor_div(a.t0 + a.n_out - 1 - gamma, tile);
+    const int64_t js0 = j_first + s0;
+    const int64_t js_end = min64(j_first + s1, j_last + 1);
+    if (js0 >= js_end) continue;
+    const int n_steps = int(js_end - js0);
+    const int r_need_max = n_steps - 1 + a.h_back + a.h_fwd;
+    const int64_t g_ring0 = gamma + (js0 - a.h_back) * tile;
+
+    // chunk r -> ring chunk slot, cooperative copy by `nthr` threads (zero fill outside)
+    auto load_chunk_sync = [&](int r, int slot, int t0, int nthr) {
+      const int64_t g0 = g_ring0 + int64_t(r) * tile;
+      T* dst = sX + slot * tile;
+      for (int e = t0; e < tile; e += nthr) {
+        const int64_t g = g0 + e;
+        const T v = (g >= lo_valid && g < hi_valid) ? xrow[g] : T(0);
+        dst[e] = v;
+        if (slot == 0) sX[RX + e] = v;
+      }
+    };
+    // issued by the slide threads (or, in the prologue, by everybody with t0/nthr of the CTA)
+    auto issue_chunk = [&](int r, int slot, int b, int t0, int nthr) {
+      const int64_t g0 = g_ring0 + int64_t(r) * tile;
+      if (g0 >= lo_valid && g0 + tile <= hi_valid) {
+        tma_bits |= 1u << b;
+        if (t0 == 0) {
+          const uint32_t bytes = uint32_t(tile) * sizeof(T);
+          fence_proxy_async();
+          mbar_expect_tx(&bars[b], slot == 0 ? 2 * bytes : bytes);
+          bulk_g2s(sX + slot * tile, xrow + g0, bytes, &bars[b]);
+          if (slot == 0) bulk_g2s(sX + RX, xrow + g0, bytes, &bars[b]);
+        }
+      } else {
+        tma_bits &= ~(1u << b);
+        load_chunk_sync(r, slot, t0, nthr);
+      }
+    };
+
+    __syncthreads();  // previous piece fully drained; barriers and table ready
+    {
+      int slot = 0;
+      for (int r = 0; r <= a.h_back + a.h_fwd; ++r) {
+        load_chunk_sync(r, slot, tid, NT);
+        slot = wrap_up(slot + 1, a.nq_x);
+      }
+    }
+    int r_issue = a.h_back + a.h_fwd + 1;
+    int slot_issue = r_issue % a.nq_x, bar_issue = r_issue % P;
+    int bar_wait = bar_issue;  // barrier of chunk (n + 1) + h_fwd while step n runs
+    // the slide threads own the TMA bookkeeping; thread `NG` (dt == 0) issues
+    for (int i = 0; i < P - 1; ++i) {
+      if (r_issue <= r_need_max) {
+        if (!is_gather) issue_chunk(r_issue, slot_issue, bar_issue, dt, ND);
+      }
+      ++r_issue;
+      slot_issue = wrap_up(slot_issue + 1, a.nq_x);
+      bar_issue = wrap_up(bar_issue + 1, P);
+    }
+    __syncthreads();
+    {  // direct evaluation of the D chunks behind chunk 0 (ring chunk slots 0 .. back-1)
+      const int sxn = a.h_back * tile;
+#pragma unroll
+      for (int k = 0; k < kMaxBoxKinds; ++k) {
+        if (k >= a.nk) break;
+        T* const sD = k == 0 ? sD0 : sD1;
+        const int RD = k == 0 ? RD0 : RD1;
+        const int back = k == 0 ? back0 : back1, n_back = back * tile, m = a.m[k];
+        for (int e = tid; e < n_back; e += NT) {
+          const int rel_i = -a.a_lo[k] - n_back + e;
+          T sum = T(0);
+          for (int q = 0; q < m; ++q) {
+            const int rel = rel_i - q * d;
+            if (rel < -a.h_back * tile) break;
+            sum += sX[wrap_both(sxn + rel, RX)];
+          }
+          sD[e] = sum;
+          if (e < tile) sD[RD + e] = sum;
+        }
+      }
+    }
+    __syncthreads();
+
+    if (!is_gather) {
+      // ------------------------------ slide warps ------------------------------
+      int slot_x = a.h_back;  // ring chunk slot of chunk n
+      int slot_d0 = back0, slot_d1 = back1;
+      for (int n = 0; n < n_steps; ++n) {
+        if (n >= 2) {  // the gather of chunk n - 2 has released the slots written below
+          const int s = n & 1;
+          mbar_wait(&empty[s], (empty_phase >> s) & 1u);
+          empty_phase ^= 1u << s;
+        }
+        if (r_issue <= r_need_max) issue_chunk(r_issue, slot_issue, bar_issue, dt, ND);
+        ++r_issue;
+        slot_issue = wrap_up(slot_issue + 1, a.nq_x);
+        bar_issue = wrap_up(bar_issue + 1, P);
+        const int sxn = slot_x * tile;
+        if (a.chain_mode) {
+          const int lanes = a.chain_lanes;
+          for (int u = dt; u < lanes * a.nk; u += ND) {
+            const int k = u >= lanes ? 1 : 0;
+            const int c = u - (k ? lanes : 0);
+            if (c >= a.chains) continue;
+            T* const sD = k ? sD1 : sD0;
+            const int RD = k ? RD1 : RD0;
+            const int slot = k ? slot_d1 : slot_d0;
+            const T* p1 = sX + wrap_up(sxn + a.cx1[k], RX) + c;
+            const T* p2 = sX + wrap_up(sxn + a.cx2[k], RX) + c;
+            T* pd = sD + slot * tile + c;
+            const T sum = sD[wrap_up(slot * tile + a.cprev[k], RD) + c];
+            const int n_el = a.q_full + (c < a.q_rem ? 1 : 0);
+            if (slot == 0) slide_chain<T, true>(p1, p2, pd, RD, d, n_el, sum);
+            else slide_chain<T, false>(p1, p2, pd, 0, d, n_el, sum);
+          }
+        } else {
+          const int chains = a.chains;
+#pragma unroll
+          for (int k = 0; k < kMaxBoxKinds; ++k) {
+            if (k >= a.nk) break;
+            T* const sD = k == 0 ? sD0 : sD1;
+            const int RD = k == 0 ? RD0 : RD1;
+            const int slot = k == 0 ? slot_d0 : slot_d1;
+            const int L = a.seg_len[k];
+            const int base1 = wrap_up(sxn + a.cx1[k], RX);
+            const T* const x1 = sX + base1;
+            const T* const x2 = sX + wrap_up(sxn + a.cx2[k], RX);
+            T* const dnew = sD + slot * tile;
+            for (int u = dt; u < chains * a.n_seg[k]; u += ND) {
+              const int s = u / chains, c = u - s * chains;
+              const int e = c + s * L * d;
+              if (e >= tile) continue;
+              T sum;
+              if (s == 0) {
+                sum = sD[wrap_up(slot * tile + a.cprev[k], RD) + c];
+              } else {
+                sum = T(0);
+                for (int q = 1; q <= a.m[k]; ++q) sum += sX[wrap_both(base1 + e - q * d, RX)];
+              }
+              const int n_el = (min(tile, e + L * d) - e + d - 1) / d;
+              if (slot == 0) slide_chain<T, true>(x1 + e, x2 + e, dnew + e, RD, d, n_el, sum);
+              else slide_chain<T, false>(x1 + e, x2 + e, dnew + e, 0, d, n_el, sum);
+            }
+          }
+        }
+        // chunk (n + 1) + h_fwd must have landed before the next slide (and the next gather)
+        if (tma_bits & (1u << bar_wait)) {
+          mbar_wait(&bars[bar_wait], (tma_phase >> bar_wait) & 1u);
+          tma_phase ^= 1u << bar_wait;
+          tma_bits &= ~(1u << bar_wait);
+        }
+        bar_wait = wrap_up(bar_wait + 1, P);
+        named_bar_sync(1, ND);  // every slide thread is done with chunk n (and any sync loads)
+        if (dt == 0) mbar_arrive(&full[n & 1]);
+        slot_x = wrap_up(slot_x + 1, a.nq_x);
+        slot_d0 = wrap_up(slot_d0 + 1, a.nq_d[0]);
+        if (a.nk > 1) slot_d1 = wrap_up(slot_d1 + 1, a.nq_d[1]);
+      }
+      // consume the releases of the last two gathers so that the parities stay in step
+      for (int n = max(n_steps - 2, 0); n < n_steps; ++n) {
+        const int s = n & 1;
+        mbar_wait(&empty[s], (empty_phase >> s) & 1u);
+        empty_phase ^= 1u << s;
+      }
+    } else {
+      // ------------------------------ gather warps ------------------------------
+      int slot_x = a.h_back, slot_d0 = back0, slot_d1 = back1;
+      int64_t cur = gamma + js0 * tile;
+      for (int n = 0; n < n_steps; ++n, cur += tile) {
+        {
+          const int s = n & 1;
+          mbar_wait(&full[s], (full_phase >> s) & 1u);
+          full_phase ^= 1u << s;
+        }
+        const bool interior = (cur - a.w_hi >= 0) && (cur + tile - a.w_lo <= a.n_total);
+        const bool all_out = (cur >= a.t0) && (cur + tile <= a.t0 + a.n_out);
+        const int32_t* const row0 = tab + a.tab_d0 + slot_d0 * a.tab_stride_d0;
+        const int32_t* const row1 = tab + a.tab_d1 + slot_d1 * a.tab_stride_d1;
+        const int32_t* const rowx = tab + a.tab_x + slot_x * a.tab_stride_x;
+        for (int i0 = gt; i0 < tile; i0 += NG * RU) {
+          const unsigned char* const lane = smem_raw + i0 * ES;
+          T acc[RU];
+#pragma unroll
+          for (int r = 0; r < RU; ++r) acc[r] = T(0);
+          auto add_term = [&](int off) {
+            const T* p = reinterpret_cast<const T*>(lane + off);
+#pragma unroll
+            for (int r = 0; r < RU; ++r) acc[r] += p[r * NG];
+          };
+          auto sub_term = [&](int off) {
+            const T* p = reinterpret_cast<const T*>(lane + off);
+#pragma unroll
+            for (int r = 0; r < RU; ++r) acc[r] -= p[r * NG];
+          };
+          int x_centre;
+          if (a.small_plan) {
+            const int4 oa = *reinterpret_cast<const int4*>(row0);
+            const int4 ob = *reinterpret_cast<const int4*>(row0 + 4);
+            const int4 oc = *reinterpret_cast<const int4*>(row1);
+            const int4 ox = *reinterpret_cast<const int4*>(rowx);
+            x_centre = ox.x;
+            switch (n_box0) {  // one indirect branch instead of a compare per term
+              case 8: add_term(ob.w);
+              case 7: add_term(ob.z);
+              case 6: add_term(ob.y);
+              case 5: add_term(ob.x);
+              case 4: add_term(oa.w);
+              case 3: add_term(oa.z);
+              case 2: add_term(oa.y);
+              case 1: add_term(oa.x);
+              default: break;
+            }
+            switch (n_box1) {
+              case 4: add_term(oc.w);
+              case 3: add_term(oc.z);
+              case 2: add_term(oc.y);
+              case 1: add_term(oc.x);
+              default: break;
+            }
+            const int xo[3] = {ox.y, ox.z, ox.w};
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              if (t < n_plus) add_term(xo[t]);
+              else if (t < n_plus + n_minus) sub_term(xo[t]);
+            }
+          } else {
+            x_centre = rowx[0];
+            int t = 0;
+#pragma unroll 1
+            for (; t + 4 <= n_box0; t += 4) {
+              const int4 o = *reinterpret_cast<const int4*>(row0 + t);
+              add_term(o.x); add_term(o.y); add_term(o.z); add_term(o.w);
+            }
+#pragma unroll 1
+            for (; t < n_box0; ++t) add_term(row0[t]);
+            t = 0;
+#pragma unroll 1
+            for (; t + 4 <= n_box1; t += 4) {
+              const int4 o = *reinterpret_cast<const int4*>(row1 + t);
+              add_term(o.x); add_term(o.y); add_term(o.z); add_term(o.w);
+            }
+#pragma unroll 1
+            for (; t < n_box1; ++t) add_term(row1[t]);
+#pragma unroll 1
+            for (t = 1; t <= n_plus; ++t) add_term(rowx[t]);
+#pragma unroll 1
+            for (t = 1 + n_plus; t <= n_plus + n_minus; ++t) sub_term(rowx[t]);
+          }
+          const T* const xc = reinterpret_cast<const T*>(lane + x_centre);
+          T* const og = orow + cur + i0;
+          if (interior && all_out) {
+#pragma unroll
+            for (int r = 0; r < RU; ++r) {
+              const T x0 = xc[r * NG];
+              og[r * NG] = x0 - (acc[r] + centre * x0) * inv_n;
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < RU; ++r) {
+              const int64_t g = cur + i0 + r * NG;
+              const T x0 = xc[r * NG];
+              const T sum = acc[r] + centre * x0;
+              const int n_in =
+                  interior ? a.n_taps : taps_in_range(a.taps, a.n_taps, g, a.n_total);
+              const T y = n_in > 0 ? x0 - sum / T(n_in) : T(0);
+              if (g >= a.t0 && g < a.t0 + a.n_out) og[r * NG] = y;
+            }
+          }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty[n & 1]);
+        slot_x = wrap_up(slot_x + 1, a.nq_x);
+        slot_d0 = wrap_up(slot_d0 + 1, a.nq_d[0]);
+        if (a.nk > 1) slot_d1 = wrap_up(slot_d1 + 1, a.nq_d[1]);
+      }
+    }
+  }
+}
+
 struct StripTuning {
-  int threads, ru, tile, prefetch, ctas_per_sm;
+  int pipe;         // 1 = producer/consumer kernel (slide warps run a chunk ahead)
+  int threads;      // gather threads (all threads when pipe = 0)
+  int slide;        // slide threads (pipe = 1)
+  int ru, tile, prefetch, ctas_per_sm;
 };
 
 template <typename T>
@@ -668,37 +1042,43 @@ int launch_strip(const FilterPlanHeader* hdr, const int32_t* h_terms, const int3
     return (v && *v) ? atoi(v) : fallback;
   };
   const int sm_budget = 227 * 1024;
-  // candidate shapes {threads, outputs per thread, tile, chunks in flight, CTAs per SM}, best
-  // first as measured on cfg2 (scripts/sweep_filter.py): big tiles amortise the two barriers
-  // of a step; the smaller ones are for tap windows whose rings would not fit
-  const StripTuning shapes[] = {{512, 4, 2048, 3, 1}, {256, 3, 768, 2, 2}, {512, 2, 1024, 4, 1},
-                                {256, 2, 512, 4, 2},  {256, 2, 512, 3, 1}, {256, 1, 256, 4, 1}};
-  StripTuning pick{0, 0, 0, 0, 0};
+  // Candidate shapes, best first as measured on cfg2 (scripts/sweep_filter.py).  The
+  // pipelined kernel needs one more chunk per ring; where that does not fit, the two-phase
+  // kernel with a big tile (which amortises its two barriers per step) comes next, then
+  // smaller tiles for wide tap windows.
+  const StripTuning shapes[] = {
+      {1, 384, 256, 4, 1536, 2, 1}, {1, 512, 256, 2, 1024, 3, 1}, {0, 512, 0, 4, 2048, 3, 1},
+      {1, 256, 256, 2, 512, 3, 1},  {0, 256, 0, 3, 768, 2, 2},    {0, 512, 0, 2, 1024, 4, 1},
+      {0, 256, 0, 2, 512, 4, 2},    {0, 256, 0, 2, 512, 3, 1},    {0, 256, 0, 1, 256, 4, 1}};
+  StripTuning pick{0, 0, 0, 0, 0, 0, 0};
   size_t pick_smem = 0;
   const int forced_tile = env_int("PARRM_FILTER_TILE", 0);
+  const int allow_pipe = env_int("PARRM_FILTER_PIPE", 1);
   for (const StripTuning& s0 : shapes) {
     StripTuning s = s0;
     if (forced_tile) {
       s.tile = forced_tile;
+      s.pipe = env_int("PARRM_FILTER_PIPE", s.pipe);
       s.threads = env_int("PARRM_FILTER_THREADS", s.threads);
+      s.slide = env_int("PARRM_FILTER_SLIDE", s.pipe ? 256 : 0);
       s.ru = env_int("PARRM_FILTER_RU", s.ru);
       s.prefetch = env_int("PARRM_FILTER_PREFETCH", s.prefetch);
       s.ctas_per_sm = env_int("PARRM_FILTER_CTAS", s.ctas_per_sm);
     }
+    if (s.pipe && !allow_pipe) continue;
     if (s.tile % (s.threads * s.ru) != 0 || s.prefetch < 1 || s.prefetch > kMaxPrefetch) continue;
     const int64_t tile = s.tile;
+    const int extra = s.pipe ? 2 : 1;  // ring chunks beyond what one step reads
     const int64_t h_back = ceil_div(int64_t(f.w_hi) + a.d, tile);
     const int64_t h_fwd = ceil_div(-int64_t(f.w_lo), tile);
-    const int64_t nq_x = h_back + h_fwd + 1 + s.prefetch;
+    const int64_t nq_x = h_back + h_fwd + extra + s.prefetch;
     int64_t elems = (nq_x + 1) * tile;
-    for (int k = 0; k < a.nk; ++k) {
-      const int64_t reach = max64(int64_t(hdr->a_max[k]) - hdr->a_min[k], a.d);
-      elems += (ceil_div(reach, tile) + 1 + 1) * tile;
-    }
     int64_t tab_ints = nq_x * round4(1 + hdr->n_plus + hdr->n_minus) + 8;
     for (int k = 0; k < kMaxBoxKinds; ++k) {
       const int64_t reach = max64(int64_t(hdr->a_max[k]) - hdr->a_min[k], a.d);
-      tab_ints += (ceil_div(reach, tile) + 1) * max64(8, round4(hdr->n_box[k]));
+      const int64_t nq_d = ceil_div(reach, tile) + extra;
+      if (k < a.nk) elems += (nq_d + 1) * tile;
+      tab_ints += nq_d * max64(8, round4(hdr->n_box[k]));
     }
     const int64_t tab_bytes = ((tab_ints * 4 + 127) / 128) * 128;
     const size_t smem = 128 + size_t(tab_bytes) + size_t(elems) * sizeof(T);
@@ -710,29 +1090,31 @@ int launch_strip(const FilterPlanHeader* hdr, const int32_t* h_terms, const int3
   if (pick.tile == 0) return PARRM_OK;  // rings do not fit: the caller falls back to the gather
 
   const int64_t tile = pick.tile;
+  const int extra = pick.pipe ? 2 : 1;
   a.tile = pick.tile;
   a.prefetch = pick.prefetch;
   a.h_back = int32_t(ceil_div(int64_t(f.w_hi) + a.d, tile));
   a.h_fwd = int32_t(ceil_div(-int64_t(f.w_lo), tile));
-  a.nq_x = a.h_back + a.h_fwd + 1 + a.prefetch;
+  a.nq_x = a.h_back + a.h_fwd + extra + a.prefetch;
   const int64_t RX = int64_t(a.nq_x) * tile;
   auto mod = [](int64_t v, int64_t ring) { return int32_t(((v % ring) + ring) % ring); };
+  const int slide_threads = pick.pipe ? pick.slide : pick.threads;
   int t = 0;
   for (int k = 0; k < a.nk; ++k) {
     a.m[k] = hdr->window[k];
     a.n_box[k] = hdr->n_box[k];
     a.a_lo[k] = hdr->a_min[k];
     const int64_t reach = max64(int64_t(hdr->a_max[k]) - hdr->a_min[k], a.d);
-    a.nq_d[k] = int32_t(ceil_div(reach, tile) + 1);
+    a.nq_d[k] = int32_t(ceil_div(reach, tile) + extra);
     const int64_t RD = int64_t(a.nq_d[k]) * tile;
     a.cx1[k] = mod(-int64_t(a.a_lo[k]), RX);
     a.cx2[k] = mod(-(int64_t(a.a_lo[k]) + int64_t(a.m[k]) * a.d), RX);
     a.cprev[k] = mod(-int64_t(a.d), RD);
-    // D-pass work split: one item per chain unless there are few chains
+    // slide work split: one item per chain unless there are few chains
     const int64_t chains = min64(a.d, tile);
     const int64_t per_chain = ceil_div(tile, a.d);
     int64_t seg = per_chain;
-    if (chains < pick.threads) {
+    if (chains * a.nk < slide_threads / 2) {
       seg = max64(9, a.m[k]) | 1;  // odd: conflict-free shared-memory strides when d is small
       seg = min64(seg, per_chain);
     }
@@ -743,6 +1125,7 @@ int launch_strip(const FilterPlanHeader* hdr, const int32_t* h_terms, const int3
   }
   for (int b = 0; b < a.n_plus + a.n_minus; ++b, ++t) a.off[t] = mod(-int64_t(h_terms[t]), RX);
   a.reinit_every = env_int("PARRM_FILTER_REINIT", 256);
+  a.piece_steps = a.reinit_every > 0 ? a.reinit_every : (1 << 30);
   a.chains = int32_t(min64(a.d, tile));
   a.chain_mode = 1;
   for (int k = 0; k < a.nk; ++k)
@@ -758,6 +1141,7 @@ int launch_strip(const FilterPlanHeader* hdr, const int32_t* h_terms, const int3
   a.tab_x = a.tab_d1 + max64(1, a.nq_d[1]) * a.tab_stride_d1;
   a.small_plan = (a.n_box[0] <= 8 && a.n_box[1] <= 4 && a.n_plus + a.n_minus <= 3) ? 1 : 0;
   a.tab_bytes = int32_t(((int64_t(a.tab_x + a.nq_x * a.tab_stride_x) * 4 + 127) / 128) * 128);
+  if (128 + size_t(a.tab_bytes) > pick_smem) return PARRM_OK;
 
   a.steps_per_chan = int32_t(ceil_div(f.n_out + tile - 1, tile));
   a.total_steps = n_chans * int64_t(a.steps_per_chan);
@@ -767,19 +1151,32 @@ int launch_strip(const FilterPlanHeader* hdr, const int32_t* h_terms, const int3
   const int64_t grid = max64(1, min64(resident, a.total_steps / 8));
 
   void (*kernel)(const StripArgs<T>) = nullptr;
+  int block = pick.threads;
+  if (pick.pipe) {
+    block = pick.threads + pick.slide;
+#define PARRM_PIPE_SHAPE(NG_, ND_, RU_) \
+  if (pick.threads == NG_ && pick.slide == ND_ && pick.ru == RU_) \
+    kernel = filter_comb_pipe_kernel<T, NG_, ND_, RU_>;
+    PARRM_PIPE_SHAPE(512, 256, 2) PARRM_PIPE_SHAPE(512, 256, 3) PARRM_PIPE_SHAPE(512, 256, 4)
+    PARRM_PIPE_SHAPE(256, 256, 2) PARRM_PIPE_SHAPE(256, 256, 4) PARRM_PIPE_SHAPE(512, 448, 2)
+    PARRM_PIPE_SHAPE(256, 128, 2) PARRM_PIPE_SHAPE(256, 128, 4) PARRM_PIPE_SHAPE(512, 128, 2)
+    PARRM_PIPE_SHAPE(768, 256, 2) PARRM_PIPE_SHAPE(384, 256, 4) PARRM_PIPE_SHAPE(768, 128, 2)
+    PARRM_PIPE_SHAPE(256, 256, 6) PARRM_PIPE_SHAPE(384, 128, 4) PARRM_PIPE_SHAPE(384, 384, 4)
+#undef PARRM_PIPE_SHAPE
+  } else {
 #define PARRM_STRIP_SHAPE(NT_, RU_) \
   if (pick.threads == NT_ && pick.ru == RU_) kernel = filter_comb_strip_kernel<T, NT_, RU_>;
-  PARRM_STRIP_SHAPE(128, 2) PARRM_STRIP_SHAPE(128, 4) PARRM_STRIP_SHAPE(128, 8)
-  PARRM_STRIP_SHAPE(256, 1) PARRM_STRIP_SHAPE(256, 2) PARRM_STRIP_SHAPE(256, 4)
-  PARRM_STRIP_SHAPE(256, 8) PARRM_STRIP_SHAPE(512, 2) PARRM_STRIP_SHAPE(512, 4)
-  PARRM_STRIP_SHAPE(256, 3) PARRM_STRIP_SHAPE(1024, 2) PARRM_STRIP_SHAPE(1024, 1)
+    PARRM_STRIP_SHAPE(256, 1) PARRM_STRIP_SHAPE(256, 2) PARRM_STRIP_SHAPE(256, 3)
+    PARRM_STRIP_SHAPE(256, 4) PARRM_STRIP_SHAPE(256, 8) PARRM_STRIP_SHAPE(512, 2)
+    PARRM_STRIP_SHAPE(512, 4) PARRM_STRIP_SHAPE(1024, 2)
 #undef PARRM_STRIP_SHAPE
+  }
   if (kernel == nullptr) return PARRM_OK;  // unknown shape: plain gather
   PARRM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      int(pick_smem)));
   PARRM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
-  kernel<<<unsigned(grid), pick.threads, pick_smem, stream>>>(a);
+  kernel<<<unsigned(grid), block, pick_smem, stream>>>(a);
   PARRM_LAUNCH_OK("filter_comb_strip_kernel");
   *launched = true;
   return PARRM_OK;

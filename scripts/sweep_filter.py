@@ -58,11 +58,12 @@ def run(label, strategy, env):
 
 run("gather", _native.PLAN_GATHER, {})
 run("auto-default", _native.PLAN_AUTO, {})
-for threads, ru, tile, pre, ctas in [
-    (256, 2, 512, 4, 2), (256, 3, 768, 2, 2), (256, 3, 768, 3, 2), (256, 4, 1024, 4, 1),
-    (512, 2, 1024, 4, 1), (1024, 1, 1024, 4, 1), (512, 4, 2048, 3, 1), (1024, 2, 2048, 3, 1),
-    (256, 8, 2048, 3, 1),
+for pipe, threads, slide, ru, tile, pre, ctas in [
+    (0, 512, 0, 4, 2048, 3, 1),
+    (1, 512, 256, 3, 1536, 2, 1), (1, 768, 256, 2, 1536, 2, 1), (1, 384, 256, 4, 1536, 2, 1),
+    (1, 768, 128, 2, 1536, 2, 1), (1, 512, 256, 2, 1024, 3, 1),
 ]:
-    run(f"t{threads} ru{ru} tile{tile} pre{pre} ctas{ctas}", _native.PLAN_AUTO,
+    run(f"pipe{pipe} t{threads}+{slide} ru{ru} tile{tile} pre{pre} ctas{ctas}", _native.PLAN_AUTO,
         {"PARRM_FILTER_TILE": tile, "PARRM_FILTER_THREADS": threads, "PARRM_FILTER_RU": ru,
-         "PARRM_FILTER_PREFETCH": pre, "PARRM_FILTER_CTAS": ctas})
+         "PARRM_FILTER_PREFETCH": pre, "PARRM_FILTER_CTAS": ctas, "PARRM_FILTER_PIPE": pipe,
+         "PARRM_FILTER_SLIDE": slide})

@@ -16,13 +16,15 @@ def _ceil_div(a, b):
 
 
 class StripModel:
-    def __init__(self, taps, desc, tile, prefetch=2, reinit_every=0, threads=256):
+    def __init__(self, taps, desc, tile, prefetch=2, reinit_every=0, threads=256, pipe=False):
         self.taps = np.asarray(taps, dtype=np.int64)
         self.n_taps = len(self.taps)
         self.w_lo = min(int(self.taps[0]), 0)
         self.w_hi = max(int(self.taps[-1]), 0)
         self.tile = tile
         self.P = prefetch
+        self.pipe = pipe
+        self.extra = 2 if pipe else 1  # ring chunks beyond what one step reads
         self.reinit_every = reinit_every
         self.d = desc["stride"]
         self.nk = len(desc["windows"])
@@ -33,11 +35,11 @@ class StripModel:
         self.centre = desc["centre"]
         self.h_back = _ceil_div(self.w_hi + self.d, tile)
         self.h_fwd = _ceil_div(-self.w_lo, tile)
-        self.nq_x = self.h_back + self.h_fwd + 1 + self.P
+        self.nq_x = self.h_back + self.h_fwd + self.extra + self.P
         self.RX = self.nq_x * tile
         self.a_lo = [int(b.min()) for b in self.boxes]
         self.nq_d = [
-            _ceil_div(max(int(b.max()) - int(b.min()), self.d), tile) + 1 for b in self.boxes
+            _ceil_div(max(int(b.max()) - int(b.min()), self.d), tile) + self.extra for b in self.boxes
         ]
         self.RD = [q * tile for q in self.nq_d]
         self.cx1 = [(-a) % self.RX for a in self.a_lo]
@@ -51,7 +53,7 @@ class StripModel:
         for k in range(self.nk):
             chains, per_chain = min(self.d, tile), _ceil_div(tile, self.d)
             seg = per_chain
-            if chains < threads:
+            if chains * self.nk < threads / 2:
                 seg = min(max(9, self.m[k]) | 1, per_chain)
             self.seg_len.append(seg)
             self.n_seg.append(_ceil_div(per_chain, seg))
@@ -92,7 +94,7 @@ class StripModel:
         tile = self.tile
         sxn = ((n + self.h_back) % self.nq_x) * tile
         for k in range(self.nk):
-            back = self.nq_d[k] - 1
+            back = self.nq_d[k] - self.extra
             n_back = back * tile
             e = np.arange(n_back)
             rel_i = -self.a_lo[k] - n_back + e
@@ -109,90 +111,115 @@ class StripModel:
             self.sD[k][self.RD[k] + within[first]] = total[first]
 
     def _piece(self, js0, js_end, gamma, t0, n_out, out):
-        tile, d = self.tile, self.d
+        tile = self.tile
         self.sX = np.full(self.RX + tile, np.nan)
         self.sD = [np.full(rd + tile, np.nan) for rd in self.RD]
+        n_steps = js_end - js0
         j_need_max = js_end - 1 + self.h_fwd
-        loaded = set()
         for j in range(js0 - self.h_back, js0 + self.h_fwd + 1):
             self._load_chunk(j, js0, gamma)
-        pending = {}
-        for j in range(js0 + self.h_fwd + 1, js0 + self.h_fwd + self.P):
+        pending = set()
+
+        def issue(j):
+            # an asynchronous chunk lands at the latest legal moment (its wait); until then
+            # its ring slot holds NaN, so both early reads and premature reuse show up
             if j <= j_need_max:
-                pending[j] = True
-        self._init_boxes(0)
-        for n in range(js_end - js0):
-            js = js0 + n
-            cur = gamma + js * tile
-            if js + self.h_fwd + self.P <= j_need_max:
-                pending[js + self.h_fwd + self.P] = True
-            # the model lands an asynchronous chunk at the latest legal moment (its wait), which
-            # checks that nothing reads it earlier; its slot must already be free when issued
-            for j in list(pending):
+                pending.add(j)
                 slot = (j - js0 + self.h_back) % self.nq_x
                 self.sX[slot * tile:(slot + 1) * tile] = np.nan
                 if slot == 0:
                     self.sX[self.RX:] = np.nan
-            if self.reinit_every and n > 0 and n % self.reinit_every == 0:
-                self._init_boxes(n)
-            sxn = ((n + self.h_back) % self.nq_x) * tile
-            # ---- slide the boxes ----
-            for k in range(self.nk):
-                back = self.nq_d[k] - 1
-                slot = (n + back) % self.nq_d[k]
-                base1 = (sxn + self.cx1[k]) % self.RX
-                base2 = (sxn + self.cx2[k]) % self.RX
-                base_prev = (slot * tile + self.cprev[k]) % self.RD[k]
-                chains = min(d, tile)
-                L = self.seg_len[k]
-                u = np.arange(chains * self.n_seg[k])
-                s_idx, c = u // chains, u % chains
-                e = c + s_idx * L * d
-                total = np.zeros(len(u))
-                first = s_idx == 0
-                total[first] = self.sD[k][base_prev + c[first]]
-                for q in range(1, self.m[k] + 1):  # direct D[i - d] for the later segments
-                    rest = ~first & (e < tile)
-                    total[rest] += self.sX[(base1 + e[rest] - q * d) % self.RX]
-                new = {}
-                for r in range(L):
-                    live = e < tile
-                    el = e[live]
-                    total[live] += self.sX[base1 + el] - self.sX[base2 + el]
-                    new.update(zip(el.tolist(), total[live].tolist()))
-                    e = e + d
-                assert len(new) == tile  # every element of the chunk written exactly once
-                el = np.fromiter(new.keys(), dtype=np.int64)
-                vals = np.fromiter(new.values(), dtype=np.float64)
-                self.sD[k][slot * tile + el] = vals
-                if slot == 0:
-                    self.sD[k][self.RD[k] + el] = vals
-            # ---- gather ----
-            i = np.arange(tile)
-            acc = np.zeros(tile)
-            for k in range(self.nk):
-                back = self.nq_d[k] - 1
-                sdn = ((n + back) % self.nq_d[k]) * tile
-                for off in self.off_box[k]:
-                    base = (sdn + off) % self.RD[k]
-                    acc += self.sD[k][base + i]
-            for off in self.off_plus:
-                acc += self.sX[(sxn + off) % self.RX + i]
-            for off in self.off_minus:
-                acc -= self.sX[(sxn + off) % self.RX + i]
-            xc = self.sX[sxn + i]
-            total = acc + self.centre * xc
-            g = cur + i
-            interior = (cur - self.w_hi >= 0) and (cur + tile - self.w_lo <= self.n_total)
-            if interior:
-                y = xc - total * (1.0 / self.n_taps)
-            else:
-                n_in = (np.searchsorted(self.taps, g, side="right")
-                        - np.searchsorted(self.taps, g - self.n_total, side="right"))
-                with np.errstate(divide="ignore", invalid="ignore"):
-                    y = np.where(n_in > 0, xc - total / n_in, 0.0)
-            keep = (g >= t0) & (g < t0 + n_out)
-            out[g[keep] - t0] = y[keep]
-            if js + self.h_fwd + 1 in pending:
-                del pending[js + self.h_fwd + 1]
-                self._load_chunk(js + self.h_fwd + 1, js0, gamma)
+
+        def land(j):
+            if j in pending:
+                pending.discard(j)
+                self._load_chunk(j, js0, gamma)
+
+        for j in range(js0 + self.h_fwd + 1, js0 + self.h_fwd + self.P):
+            issue(j)
+        self._init_boxes(0)
+        if not self.pipe:
+            for n in range(n_steps):
+                js = js0 + n
+                issue(js + self.h_fwd + self.P)
+                if self.reinit_every and n > 0 and n % self.reinit_every == 0:
+                    self._init_boxes(n)
+                self._slide(n)
+                self._gather(n, gamma + js * tile, t0, n_out, out)
+                land(js + self.h_fwd + 1)
+        else:
+            # the slide warps run as far ahead as the hand-off barriers allow: slide(n + 1)
+            # (and its TMA issue) completes before gather(n) starts
+            def slide_step(n):
+                issue(js0 + n + self.h_fwd + self.P)
+                self._slide(n)
+                land(js0 + n + 1 + self.h_fwd)
+
+            slide_step(0)
+            for n in range(n_steps):
+                if n + 1 < n_steps:
+                    slide_step(n + 1)
+                self._gather(n, gamma + (js0 + n) * tile, t0, n_out, out)
+
+    def _slide(self, n):
+        tile, d = self.tile, self.d
+        sxn = ((n + self.h_back) % self.nq_x) * tile
+        for k in range(self.nk):
+            back = self.nq_d[k] - self.extra
+            slot = (n + back) % self.nq_d[k]
+            base1 = (sxn + self.cx1[k]) % self.RX
+            base2 = (sxn + self.cx2[k]) % self.RX
+            base_prev = (slot * tile + self.cprev[k]) % self.RD[k]
+            chains = min(d, tile)
+            L = self.seg_len[k]
+            u = np.arange(chains * self.n_seg[k])
+            s_idx, c = u // chains, u % chains
+            e = c + s_idx * L * d
+            total = np.zeros(len(u))
+            first = s_idx == 0
+            total[first] = self.sD[k][base_prev + c[first]]
+            for q in range(1, self.m[k] + 1):  # direct D[i - d] for the later segments
+                rest = ~first & (e < tile)
+                total[rest] += self.sX[(base1 + e[rest] - q * d) % self.RX]
+            new = {}
+            for r in range(L):
+                live = e < tile
+                el = e[live]
+                total[live] += self.sX[base1 + el] - self.sX[base2 + el]
+                new.update(zip(el.tolist(), total[live].tolist()))
+                e = e + d
+            assert len(new) == tile  # every element of the chunk written exactly once
+            el = np.fromiter(new.keys(), dtype=np.int64)
+            vals = np.fromiter(new.values(), dtype=np.float64)
+            self.sD[k][slot * tile + el] = vals
+            if slot == 0:
+                self.sD[k][self.RD[k] + el] = vals
+
+    def _gather(self, n, cur, t0, n_out, out):
+        tile = self.tile
+        sxn = ((n + self.h_back) % self.nq_x) * tile
+        i = np.arange(tile)
+        acc = np.zeros(tile)
+        for k in range(self.nk):
+            back = self.nq_d[k] - self.extra
+            sdn = ((n + back) % self.nq_d[k]) * tile
+            for off in self.off_box[k]:
+                base = (sdn + off) % self.RD[k]
+                acc += self.sD[k][base + i]
+        for off in self.off_plus:
+            acc += self.sX[(sxn + off) % self.RX + i]
+        for off in self.off_minus:
+            acc -= self.sX[(sxn + off) % self.RX + i]
+        xc = self.sX[sxn + i]
+        total = acc + self.centre * xc
+        g = cur + i
+        interior = (cur - self.w_hi >= 0) and (cur + tile - self.w_lo <= self.n_total)
+        if interior:
+            y = xc - total * (1.0 / self.n_taps)
+        else:
+            n_in = (np.searchsorted(self.taps, g, side="right")
+                    - np.searchsorted(self.taps, g - self.n_total, side="right"))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                y = np.where(n_in > 0, xc - total / n_in, 0.0)
+        keep = (g >= t0) & (g < t0 + n_out)
+        out[g[keep] - t0] = y[keep]

@@ -108,10 +108,12 @@ MODEL_CASES = [
 ]
 
 
+@pytest.mark.parametrize("pipe", [False, True])
 @pytest.mark.parametrize("spec", MODEL_CASES)
-def test_strip_design_matches_oracle(spec):
+def test_strip_design_matches_oracle(spec, pipe):
     """Ring slots, mirror chunk, sliding boxes, piece boundaries and edge counts of the strip
-    kernel (NumPy model with the kernel's index arithmetic) against the oracle's direct sum."""
+    kernels (NumPy model with their index arithmetic) against the oracle's direct sum.
+    ``pipe`` models the producer/consumer kernel with the slide running a full chunk ahead."""
     case, n_total, tile, prefetch, gamma, pieces, reinit, chunk = spec
     period, phw, hw, omit, direction = CASES[case]
     taps = oracle.tap_offsets(period, period / 50 if phw is None else phw, hw, omit, direction)
@@ -119,7 +121,7 @@ def test_strip_design_matches_oracle(spec):
     rng = np.random.default_rng(case)
     x = rng.standard_normal((1, n_total)) + 3.0
     want = oracle.apply_filter_direct(x, taps)[0]
-    model = StripModel(taps, desc, tile, prefetch, reinit)
+    model = StripModel(taps, desc, tile, prefetch, 0 if pipe else reinit, pipe=pipe)
     if chunk is None:
         got = model.run(x[0], 0, 0, n_total, n_total, gamma, pieces)
     else:
