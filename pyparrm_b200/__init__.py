@@ -10,6 +10,8 @@ __version__ = "1.2.0dev+b200.r1"
 from .data import get_example_data_paths
 from .parrm import PARRM
 from ._engine import pinned_empty
+from ._sharding import disable as disable_sharding
+from ._sharding import enable as enable_sharding
 
 
 def install_as_pyparrm() -> None:
@@ -21,4 +23,5 @@ def install_as_pyparrm() -> None:
     sys.modules.setdefault("pyparrm.parrm", sys.modules[__name__ + ".parrm"])
 
 
-__all__ = ["PARRM", "get_example_data_paths", "pinned_empty", "install_as_pyparrm", "__version__"]
+__all__ = ["PARRM", "get_example_data_paths", "pinned_empty", "install_as_pyparrm",
+           "enable_sharding", "disable_sharding", "__version__"]

@@ -406,6 +406,25 @@ class DeviceEngine:
             self.launches += 1
         return d_out
 
+    def filter_host_window(self, chunk: np.ndarray, taps: np.ndarray, x0: int, t0: int, t1: int,
+                           n_total: int) -> np.ndarray:
+        """Time shard of ``filter_data``: ``chunk`` holds samples ``[x0, x0 + chunk.shape[1])`` of
+        a recording of ``n_total`` samples (the outputs' tap-window halo included); returns the
+        outputs for global times ``[t0, t1)``.  Used when channels are fewer than ranks."""
+        t = self.torch
+        chunk, _ = self._as_float_array(chunk, allow_f32=False)
+        n_chans, n_x = chunk.shape
+        with self._lock, t.cuda.device(self.device):
+            h_plan, d_plan, _ = self._plan(taps, _native.F64)
+            d_x = t.from_numpy(chunk).to(self.device)
+            d_out = t.empty((n_chans, t1 - t0), dtype=t.float64, device=self.device)
+            check(lib.parrm_filter_apply(
+                _vp(d_x.data_ptr()), n_x, x0, n_x, _vp(d_out.data_ptr()), t1 - t0, t0, t1 - t0,
+                n_total, n_chans, _vp(d_plan.data_ptr()), _vp(h_plan.ctypes.data), _native.F64,
+                self._stream_ptr(t.cuda.current_stream())), "parrm_filter_apply")
+            self.launches += 1
+            return d_out.cpu().numpy()
+
     def filter_host(self, data: np.ndarray, taps: np.ndarray, precision: str = "fp64",
                     strategy: int | None = None) -> np.ndarray:
         """``filter_data`` body (parrm.py:861-869): NumPy [C, T] in, float64 NumPy [C, T] out."""

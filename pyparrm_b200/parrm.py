@@ -28,7 +28,7 @@ from multiprocessing import cpu_count
 
 import numpy as np
 
-from . import _engine
+from . import _engine, _sharding
 from ._neldermead import fmin_batch
 
 np.seterr(all="ignore")  # the reference silences divide/invalid globally (parrm.py:15)
@@ -314,9 +314,19 @@ class PARRM:
     def _evaluate(self, periods, tile, bandwidth, lambda_) -> np.ndarray:
         return _engine.get_engine().evaluate(tile, periods, bandwidth, lambda_, self._n_chans)
 
+    def _evaluate_grid(self, periods, tile, bandwidth, lambda_) -> np.ndarray:
+        """The data-parallel map of the reference (pqdm, parrm.py:445-454).  Under
+        ``pyparrm_b200.enable_sharding()`` the candidates are split over the ranks and the fit
+        errors exchanged with one all-gather."""
+        if _sharding.active():
+            return _sharding.evaluate_sharded(
+                lambda block: self._evaluate(block, tile, bandwidth, lambda_), periods
+            )
+        return self._evaluate(periods, tile, bandwidth, lambda_)
+
     def _optimise_period_estimate_first_run(self, periods, tile, bandwidth, lambda_):
         """Evaluate the grid and rank it (reference parrm.py:407-465)."""
-        fit_error = self._evaluate(periods, tile, bandwidth, lambda_)
+        fit_error = self._evaluate_grid(periods, tile, bandwidth, lambda_)
         order = fit_error.argsort()
         fit_error = fit_error[order]
         periods = periods[order[np.isfinite(fit_error)]]

@@ -50,3 +50,10 @@ class OracleEngine:
 
     def filter_host(self, data, taps, precision="fp64"):
         return oracle.apply_filter_direct(np.asarray(data, dtype=np.float64), taps)
+
+    def filter_host_window(self, chunk, taps, x0, t0, t1, n_total):
+        """Time shard: zero-pad the chunk into place and keep the requested outputs."""
+        chunk = np.asarray(chunk, dtype=np.float64)
+        full = np.zeros((chunk.shape[0], n_total))
+        full[:, x0:x0 + chunk.shape[1]] = chunk
+        return oracle.apply_filter_direct(full, taps)[:, t0:t1]

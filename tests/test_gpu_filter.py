@@ -189,3 +189,20 @@ def test_public_api_filter_matches_golden(golden, gpu_engine):
     assert parrm._filter_half_width == int(g["default_half_width"])
     assert np.array_equal(np.flatnonzero(parrm.filter < 0) - parrm._filter_half_width,
                           g["default_taps"])
+
+
+def test_time_shards_stitch_to_the_whole(gpu_engine):
+    """fewer channels than GPUs -> time chunks with halos.  The shards of all
+    ranks (run one after the other on this GPU) stitch to the unsharded result."""
+    from pyparrm_b200 import _sharding
+
+    x = make_recording(1, 123_457, 2000, 130, seed=11)
+    for direction in ("both", "past", "future"):
+        taps = oracle.tap_offsets(2000 / 130, 0.3, 2000, 0, direction)
+        want = oracle.apply_filter_direct(x, taps)
+        w_lo, w_hi = min(int(taps[0]), 0), max(int(taps[-1]), 0)
+        got = np.full_like(x, np.nan)
+        for c0, c1, t0, t1, x0, x1 in _sharding.channel_or_time_shards(1, x.shape[1], 4, w_lo, w_hi):
+            got[c0:c1, t0:t1] = gpu_engine.filter_host_window(x[c0:c1, x0:x1], taps, x0, t0, t1,
+                                                              x.shape[1])
+        assert rel_err(got, want, np.abs(x).max()) <= 1e-13
