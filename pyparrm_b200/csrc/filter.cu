@@ -267,8 +267,17 @@ __device__ unsigned long long g_strip_timing[8];
       tick__ = now__;                                                \
     }                                                                \
   } while (0)
+#define PIPE_TICK(who, slot)                                         \
+  do {                                                               \
+    if (blockIdx.x == 0 && tid == (who)) {                           \
+      const long long now__ = clock64();                             \
+      atomicAdd(&g_strip_timing[slot], (unsigned long long)(now__ - ptick__)); \
+      ptick__ = now__;                                               \
+    }                                                                \
+  } while (0)
 #else
 #define STRIP_TICK(slot) do {} while (0)
+#define PIPE_TICK(who, slot) do {} while (0)
 #endif
 
 // One chain of a comb box: D[e] = D[e - d] + x[e] - x[e - m d] for the chain's n elements, the
@@ -696,8 +705,10 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
     }
     fence_mbar_init();
   }
-  {  // gather address table (see filter_comb_strip_kernel)
+  {  // gather address table (see filter_comb_strip_kernel); padding entries stay valid offsets
     const int x_base = 128 + a.tab_bytes;
+    for (int i = tid; i < a.tab_bytes / 4; i += NT) tab[i] = x_base;
+    __syncthreads();
     const int d0_base = x_base + (RX + tile) * ES;
     const int d1_base = d0_base + (RD0 + tile) * ES;
     const int n_x_terms = 1 + n_plus + n_minus;
@@ -822,17 +833,22 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
       // ------------------------------ slide warps ------------------------------
       int slot_x = a.h_back;  // ring chunk slot of chunk n
       int slot_d0 = back0, slot_d1 = back1;
+#ifdef PARRM_STRIP_TIMING
+      long long ptick__ = clock64();
+#endif
       for (int n = 0; n < n_steps; ++n) {
         if (n >= 2) {  // the gather of chunk n - 2 has released the slots written below
           const int s = n & 1;
           mbar_wait(&empty[s], (empty_phase >> s) & 1u);
           empty_phase ^= 1u << s;
         }
+        PIPE_TICK(NG, 4);
         if (r_issue <= r_need_max) issue_chunk(r_issue, slot_issue, bar_issue, dt, ND);
         ++r_issue;
         slot_issue = wrap_up(slot_issue + 1, a.nq_x);
         bar_issue = wrap_up(bar_issue + 1, P);
         const int sxn = slot_x * tile;
+#ifndef PARRM_DEBUG_SKIP_SLIDE
         if (a.chain_mode) {
           const int lanes = a.chain_lanes;
           for (int u = dt; u < lanes * a.nk; u += ND) {
@@ -880,6 +896,8 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
             }
           }
         }
+#endif
+        PIPE_TICK(NG, 5);
         // chunk (n + 1) + h_fwd must have landed before the next slide (and the next gather)
         if (tma_bits & (1u << bar_wait)) {
           mbar_wait(&bars[bar_wait], (tma_phase >> bar_wait) & 1u);
@@ -887,8 +905,10 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
           tma_bits &= ~(1u << bar_wait);
         }
         bar_wait = wrap_up(bar_wait + 1, P);
+        PIPE_TICK(NG, 6);
         named_bar_sync(1, ND);  // every slide thread is done with chunk n (and any sync loads)
         if (dt == 0) mbar_arrive(&full[n & 1]);
+        PIPE_TICK(NG, 7);
         slot_x = wrap_up(slot_x + 1, a.nq_x);
         slot_d0 = wrap_up(slot_d0 + 1, a.nq_d[0]);
         if (a.nk > 1) slot_d1 = wrap_up(slot_d1 + 1, a.nq_d[1]);
@@ -903,17 +923,22 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
       // ------------------------------ gather warps ------------------------------
       int slot_x = a.h_back, slot_d0 = back0, slot_d1 = back1;
       int64_t cur = gamma + js0 * tile;
+#ifdef PARRM_STRIP_TIMING
+      long long ptick__ = clock64();
+#endif
       for (int n = 0; n < n_steps; ++n, cur += tile) {
         {
           const int s = n & 1;
           mbar_wait(&full[s], (full_phase >> s) & 1u);
           full_phase ^= 1u << s;
         }
+        PIPE_TICK(0, 0);
         const bool interior = (cur - a.w_hi >= 0) && (cur + tile - a.w_lo <= a.n_total);
         const bool all_out = (cur >= a.t0) && (cur + tile <= a.t0 + a.n_out);
         const int32_t* const row0 = tab + a.tab_d0 + slot_d0 * a.tab_stride_d0;
         const int32_t* const row1 = tab + a.tab_d1 + slot_d1 * a.tab_stride_d1;
         const int32_t* const rowx = tab + a.tab_x + slot_x * a.tab_stride_x;
+#ifndef PARRM_DEBUG_SKIP_GATHER
         for (int i0 = gt; i0 < tile; i0 += NG * RU) {
           const unsigned char* const lane = smem_raw + i0 * ES;
           T acc[RU];
@@ -1004,8 +1029,11 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
             }
           }
         }
+#endif
+        PIPE_TICK(0, 1);
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&empty[n & 1]);
+        PIPE_TICK(0, 2);
         slot_x = wrap_up(slot_x + 1, a.nq_x);
         slot_d0 = wrap_up(slot_d0 + 1, a.nq_d[0]);
         if (a.nk > 1) slot_d1 = wrap_up(slot_d1 + 1, a.nq_d[1]);
@@ -1015,7 +1043,7 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
 }
 
 struct StripTuning {
-  int pipe;         // 1 = producer/consumer kernel (slide warps run a chunk ahead)
+  int pipe;         // 0 two-phase kernel, 1 producer/consumer (slide warps a chunk ahead)
   int threads;      // gather threads (all threads when pipe = 0)
   int slide;        // slide threads (pipe = 1)
   int ru, tile, prefetch, ctas_per_sm;
@@ -1047,7 +1075,7 @@ int launch_strip(const FilterPlanHeader* hdr, const int32_t* h_terms, const int3
   // kernel with a big tile (which amortises its two barriers per step) comes next, then
   // smaller tiles for wide tap windows.
   const StripTuning shapes[] = {
-      {1, 384, 256, 4, 1536, 2, 1}, {1, 512, 256, 2, 1024, 3, 1}, {0, 512, 0, 4, 2048, 3, 1},
+      {1, 256, 256, 6, 1536, 2, 1}, {1, 512, 256, 2, 1024, 3, 1}, {0, 512, 0, 4, 2048, 3, 1},
       {1, 256, 256, 2, 512, 3, 1},  {0, 256, 0, 3, 768, 2, 2},    {0, 512, 0, 2, 1024, 4, 1},
       {0, 256, 0, 2, 512, 4, 2},    {0, 256, 0, 2, 512, 3, 1},    {0, 256, 0, 1, 256, 4, 1}};
   StripTuning pick{0, 0, 0, 0, 0, 0, 0};
@@ -1060,7 +1088,7 @@ int launch_strip(const FilterPlanHeader* hdr, const int32_t* h_terms, const int3
       s.tile = forced_tile;
       s.pipe = env_int("PARRM_FILTER_PIPE", s.pipe);
       s.threads = env_int("PARRM_FILTER_THREADS", s.threads);
-      s.slide = env_int("PARRM_FILTER_SLIDE", s.pipe ? 256 : 0);
+      s.slide = env_int("PARRM_FILTER_SLIDE", s.pipe == 1 ? 256 : 0);
       s.ru = env_int("PARRM_FILTER_RU", s.ru);
       s.prefetch = env_int("PARRM_FILTER_PREFETCH", s.prefetch);
       s.ctas_per_sm = env_int("PARRM_FILTER_CTAS", s.ctas_per_sm);
@@ -1098,7 +1126,7 @@ int launch_strip(const FilterPlanHeader* hdr, const int32_t* h_terms, const int3
   a.nq_x = a.h_back + a.h_fwd + extra + a.prefetch;
   const int64_t RX = int64_t(a.nq_x) * tile;
   auto mod = [](int64_t v, int64_t ring) { return int32_t(((v % ring) + ring) % ring); };
-  const int slide_threads = pick.pipe ? pick.slide : pick.threads;
+  const int slide_threads = pick.pipe == 1 ? pick.slide : pick.threads;
   int t = 0;
   for (int k = 0; k < a.nk; ++k) {
     a.m[k] = hdr->window[k];
@@ -1152,7 +1180,7 @@ int launch_strip(const FilterPlanHeader* hdr, const int32_t* h_terms, const int3
 
   void (*kernel)(const StripArgs<T>) = nullptr;
   int block = pick.threads;
-  if (pick.pipe) {
+  if (pick.pipe == 1) {
     block = pick.threads + pick.slide;
 #define PARRM_PIPE_SHAPE(NG_, ND_, RU_) \
   if (pick.threads == NG_ && pick.slide == ND_ && pick.ru == RU_) \

@@ -73,6 +73,27 @@ __device__ __forceinline__ void cpow(double c1, double s1, int n, double& c, dou
   }
 }
 
+// Shared-memory slot of channel c (0..63) of sample k in a Y tile.  A GEMM thread reads its
+// four channels as two 16-byte loads (c = 4 cg .. 4 cg + 3); with the plain [k][c] layout the
+// 16 column groups of a quarter-warp would span 256 bytes per load (2-way bank conflict), so
+// the two halves of every group live in separate 128-byte planes.
+__device__ __forceinline__ int y_slot(int k, int c) {
+  return k * kChanTile + ((c >> 1) & 1) * (kChanTile / 2) + (c >> 2) * 2 + (c & 1);
+}
+// 8-byte asynchronous global -> shared copy (LDGSTS); src_bytes = 0 writes zeros.
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst_smem)),
+               "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 __global__ void __launch_bounds__(kAccThreads, 2)
 eval_accumulate_kernel(const double* __restrict__ y, const int64_t* __restrict__ indices,
                        const double* __restrict__ periods, double* __restrict__ ws,
@@ -80,8 +101,8 @@ eval_accumulate_kernel(const double* __restrict__ y, const int64_t* __restrict__
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* s_cs = reinterpret_cast<double2*>(smem_raw);                 // [kSuper] (cos, sin)
   double* s_w = reinterpret_cast<double*>(smem_raw + kSuper * 16);      // [kKT][kRowStride]
-  double* s_y = s_w + kKT * kRowStride;                                  // [kKT][kChanTile]
-  double* s_red = s_y + kKT * kChanTile;                                // [8 warps][2*H]
+  double* s_y = s_w + kKT * kRowStride;      // 2 x [kKT][2 planes][16 column groups][2], see y_slot
+  double* s_red = s_y + 2 * kKT * kChanTile;                            // [8 warps][2*H]
   constexpr int H = kHMax;
 
   const int tid = threadIdx.x;
@@ -113,6 +134,22 @@ eval_accumulate_kernel(const double* __restrict__ y, const int64_t* __restrict__
   for (int r = 0; r < kRowTile; ++r)
 #pragma unroll
     for (int c = 0; c < kColTile; ++c) acc[r][c] = 0.0;
+
+  // Y tiles (sample-major rows of the standardised data) stream through two shared-memory
+  // buffers with cp.async, one tile ahead of the GEMM, so their global-memory latency is
+  // hidden behind the harmonic generation and the FMA tiles.
+  auto stage_y = [&](int buf, int64_t n_tile) {
+    double* dst = s_y + buf * (kKT * kChanTile);
+    for (int e = tid; e < kKT * kChanTile; e += kAccThreads) {
+      const int k = e / kChanTile, c = e % kChanTile;
+      const int64_t n = n_tile + k;
+      const bool ok = n < n_end && c < n_chan_here;
+      cp_async8(dst + y_slot(k, c), ok ? y + n * sh.ld_y + chan0 + c : y, ok ? 8 : 0);
+    }
+    cp_async_commit();
+  };
+  int y_buf = 0;
+  if (n_begin < n_end) stage_y(0, n_begin);
 
   for (int64_t n_super = n_begin; n_super < n_end; n_super += kSuper) {
     // one accurate sincos per sample of this batch; invalid lanes hold (0, 0)
@@ -156,24 +193,25 @@ eval_accumulate_kernel(const double* __restrict__ y, const int64_t* __restrict__
         if (gg == kGroups - 1)
           for (int r = n_rows; r < kRowsPad; ++r) wrow[r] = 0.0;
       }
-      // ---- stage the Y tile (sample-major rows of n_chan_here doubles) ----
-      for (int e = tid; e < kKT * kChanTile; e += kAccThreads) {
-        const int k = e / kChanTile, c = e % kChanTile;
-        const int64_t n = n_tile + k;
-        s_y[e] = (n < n_end && c < n_chan_here) ? y[n * sh.ld_y + chan0 + c] : 0.0;
+      // ---- this tile's Y has been in flight since the previous tile; start the next one ----
+      if (n_tile + kKT < n_end) {
+        stage_y(y_buf ^ 1, n_tile + kKT);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
       }
       __syncthreads();
       // ---- B += W' Y over this K-half's 32 samples ----
       if (rows_live) {
         const double* wp = s_w + (kh * (kKT / 2)) * kRowStride + rg * kRowTile;
-        const double* yp = s_y + (kh * (kKT / 2)) * kChanTile + cg * kColTile;
+        const double* yp = s_y + y_buf * (kKT * kChanTile) + (kh * (kKT / 2)) * kChanTile + cg * 2;
 #pragma unroll 4
         for (int k = 0; k < kKT / 2; ++k) {
           const double2 w01 = *reinterpret_cast<const double2*>(wp + k * kRowStride);
           const double2 w23 = *reinterpret_cast<const double2*>(wp + k * kRowStride + 2);
           const double2 w45 = *reinterpret_cast<const double2*>(wp + k * kRowStride + 4);
           const double2 y01 = *reinterpret_cast<const double2*>(yp + k * kChanTile);
-          const double2 y23 = *reinterpret_cast<const double2*>(yp + k * kChanTile + 2);
+          const double2 y23 = *reinterpret_cast<const double2*>(yp + k * kChanTile + kChanTile / 2);
           const double wv[kRowTile] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y};
           const double yv[kColTile] = {y01.x, y01.y, y23.x, y23.y};
 #pragma unroll
@@ -183,6 +221,7 @@ eval_accumulate_kernel(const double* __restrict__ y, const int64_t* __restrict__
         }
       }
       __syncthreads();
+      y_buf ^= 1;
     }
   }
 
@@ -511,7 +550,7 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
   double* ws = static_cast<double*>(d_workspace);
   dim3 grid((unsigned)n_periods, (unsigned)sh.n_splits, (unsigned)sh.n_chan_tiles);
   const size_t smem =
-      size_t(kSuper * 16 + (kKT * kRowStride + kKT * kChanTile + 8 * 2 * kHMax) * sizeof(double));
+      size_t(kSuper * 16 + (kKT * kRowStride + 2 * kKT * kChanTile + 8 * 2 * kHMax) * sizeof(double));
   PARRM_CUDA_OK(cudaFuncSetAttribute(eval_accumulate_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   eval_accumulate_kernel<<<grid, kAccThreads, smem, s>>>(d_y, d_indices, d_periods, ws, sh);

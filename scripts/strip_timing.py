@@ -25,10 +25,16 @@ eng = _engine.get_engine()
 d_x = torch.randn((C, T), dtype=torch.float64, device="cuda")
 d_y = torch.empty_like(d_x)
 names = ["issue", "dpass(own)", "bar1", "gather", "wait+ctr", "bar2", "-", "-"]
+pipe_names = ["g:wait_full", "g:gather", "g:arrive", "-", "s:wait_empty", "s:issue+slide", "s:wait_tma",
+              "s:bar+arrive"]
 for shape in sys.argv[1:] or ["512,4,2048,3,1"]:
-    th, ru, tile, pre, ctas = shape.split(",")
+    parts = shape.split(",")
+    pipe = len(parts) == 6
+    th, ru, tile, pre, ctas = parts[:5]
     os.environ.update(PARRM_FILTER_TILE=tile, PARRM_FILTER_THREADS=th, PARRM_FILTER_RU=ru,
-                      PARRM_FILTER_PREFETCH=pre, PARRM_FILTER_CTAS=ctas)
+                      PARRM_FILTER_PREFETCH=pre, PARRM_FILTER_CTAS=ctas,
+                      PARRM_FILTER_PIPE="1" if pipe else "0",
+                      PARRM_FILTER_SLIDE=parts[5] if pipe else "0")
     eng.filter_device(d_x, taps, d_out=d_y)
     torch.cuda.synchronize()
     buf = (ctypes.c_ulonglong * 8)()
@@ -40,5 +46,5 @@ for shape in sys.argv[1:] or ["512,4,2048,3,1"]:
     n_ctas = 148 * int(ctas)
     steps = (C * ((T + 2 * int(tile) - 2) // int(tile))) / n_ctas
     print(shape, "steps/CTA ~%.0f" % steps,
-          {n: round(v / steps) for n, v in zip(names, vals) if n != "-"},
+          {n: round(v / steps) for n, v in zip(pipe_names if pipe else names, vals) if n != "-"},
           "total/step %.0f" % (vals.sum() / steps))
