@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from pyparrm_b200 import _native  # noqa: E402
 
-_native.LIB_PATH = os.path.join(ROOT, "build", "libparrm_b200_timing.so")
+_native.LIB_PATH = os.environ.get("PARRM_TIMING_LIB", os.path.join(ROOT, "build", "libparrm_b200_timing.so"))
 _native.lib = _native._load()
 from pyparrm_b200 import _engine  # noqa: E402
 

@@ -206,3 +206,25 @@ def test_time_shards_stitch_to_the_whole(gpu_engine):
             got[c0:c1, t0:t1] = gpu_engine.filter_host_window(x[c0:c1, x0:x1], taps, x0, t0, t1,
                                                               x.shape[1])
         assert rel_err(got, want, np.abs(x).max()) <= 1e-13
+
+
+@pytest.mark.parametrize("name, fs, fa, n_chans, n, hw, direction", [
+    ("cfg3 ECoG 1 kHz / 145 Hz, default half-width", 1000, 145, 6, 400_000, 2469, "both"),
+    ("cfg4 Neuropixels-like 30 kHz / 130 Hz, causal", 30000, 130, 6, 600_000, 2311, "past"),
+    ("cfg4, the other one-sided direction", 30000, 130, 3, 300_000, 2311, "future"),
+])
+def test_baseline_config_shapes(gpu_engine, name, fs, fa, n_chans, n, hw, direction):
+    """The tap structures of BASELINE configs 3 and 4 (stride 200 with windows 25/12; stride 1
+    runs of 9 consecutive taps) at reduced channel counts, against the oracle and the plain
+    gather kernel."""
+    x = make_recording(n_chans, n, fs, fa, seed=17)
+    per = fs / fa * (1 + 3e-6)
+    taps = oracle.tap_offsets(per, per / 50, hw, 0, direction)
+    _, desc = _native.plan_filter(taps)
+    assert desc["kind"] == 1, name
+    out = gpu_engine.filter_host(x, taps)
+    ref = gpu_engine.filter_host(x, taps, strategy=_native.PLAN_GATHER)
+    assert rel_err(out, ref, np.abs(x).max()) <= 1e-13
+    want = oracle.apply_filter_direct(x[:2], taps)
+    assert rel_err(out[:2], want, np.abs(x).max()) <= 1e-13
+    assert rel_err(ref[:2], want, np.abs(x).max()) <= 1e-13
