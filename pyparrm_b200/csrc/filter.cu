@@ -307,6 +307,34 @@ __device__ __forceinline__ void slide_chain(const T* __restrict__ p1, const T* _
   }
 }
 
+// The same chain for an X ring without a mirror chunk: positions i1 / i2 (ring elements) wrap.
+template <typename T, bool MIRROR>
+__device__ __forceinline__ void slide_chain_ring(const T* __restrict__ sX, int RX, int i1, int i2,
+                                                 T* __restrict__ pd, int mirror, int d, int n,
+                                                 T sum) {
+  auto at = [&](int pos) { return sX[pos >= RX ? pos - RX : pos]; };
+  int q = 0;
+#pragma unroll 1
+  for (; q + 4 <= n; q += 4) {
+    const T d0 = at(i1) - at(i2);
+    const T d1 = at(i1 + d) - at(i2 + d);
+    const T d2 = at(i1 + 2 * d) - at(i2 + 2 * d);
+    const T d3 = at(i1 + 3 * d) - at(i2 + 3 * d);
+    sum += d0; pd[0] = sum;     if (MIRROR) pd[mirror] = sum;
+    sum += d1; pd[d] = sum;     if (MIRROR) pd[mirror + d] = sum;
+    sum += d2; pd[2 * d] = sum; if (MIRROR) pd[mirror + 2 * d] = sum;
+    sum += d3; pd[3 * d] = sum; if (MIRROR) pd[mirror + 3 * d] = sum;
+    i1 += 4 * d; i2 += 4 * d; pd += 4 * d;
+  }
+#pragma unroll 1
+  for (; q < n; ++q) {
+    sum += at(i1) - at(i2);
+    pd[0] = sum;
+    if (MIRROR) pd[mirror] = sum;
+    i1 += d; i2 += d; pd += d;
+  }
+}
+
 template <typename T, int NT, int RU>
 __global__ void __launch_bounds__(NT) filter_comb_strip_kernel(const StripArgs<T> a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -678,7 +706,7 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
   const int tile = a.tile;
   const int RX = a.nq_x * tile;
   T* const sX = reinterpret_cast<T*>(smem_raw + 128 + a.tab_bytes);
-  T* const sD0 = sX + RX + tile;
+  T* const sD0 = sX + RX;  // the X ring has no mirror chunk here: X reads wrap per lane
   const int RD0 = a.nq_d[0] * tile;
   T* const sD1 = sD0 + RD0 + tile;
   const int RD1 = a.nk > 1 ? a.nq_d[1] * tile : 0;
@@ -709,7 +737,7 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
     const int x_base = 128 + a.tab_bytes;
     for (int i = tid; i < a.tab_bytes / 4; i += NT) tab[i] = x_base;
     __syncthreads();
-    const int d0_base = x_base + (RX + tile) * ES;
+    const int d0_base = x_base + RX * ES;
     const int d1_base = d0_base + (RD0 + tile) * ES;
     const int n_x_terms = 1 + n_plus + n_minus;
     for (int i = tid; i < a.nq_d[0] * n_box0; i += NT) {
@@ -764,7 +792,6 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
         const int64_t g = g0 + e;
         const T v = (g >= lo_valid && g < hi_valid) ? xrow[g] : T(0);
         dst[e] = v;
-        if (slot == 0) sX[RX + e] = v;
       }
     };
     // issued by the slide threads (or, in the prologue, by everybody with t0/nthr of the CTA)
@@ -775,9 +802,8 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
         if (t0 == 0) {
           const uint32_t bytes = uint32_t(tile) * sizeof(T);
           fence_proxy_async();
-          mbar_expect_tx(&bars[b], slot == 0 ? 2 * bytes : bytes);
+          mbar_expect_tx(&bars[b], bytes);
           bulk_g2s(sX + slot * tile, xrow + g0, bytes, &bars[b]);
-          if (slot == 0) bulk_g2s(sX + RX, xrow + g0, bytes, &bars[b]);
         }
       } else {
         tma_bits &= ~(1u << b);
@@ -858,13 +884,13 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
             T* const sD = k ? sD1 : sD0;
             const int RD = k ? RD1 : RD0;
             const int slot = k ? slot_d1 : slot_d0;
-            const T* p1 = sX + wrap_up(sxn + a.cx1[k], RX) + c;
-            const T* p2 = sX + wrap_up(sxn + a.cx2[k], RX) + c;
+            const int i1 = wrap_up(sxn + a.cx1[k], RX) + c;
+            const int i2 = wrap_up(sxn + a.cx2[k], RX) + c;
             T* pd = sD + slot * tile + c;
             const T sum = sD[wrap_up(slot * tile + a.cprev[k], RD) + c];
             const int n_el = a.q_full + (c < a.q_rem ? 1 : 0);
-            if (slot == 0) slide_chain<T, true>(p1, p2, pd, RD, d, n_el, sum);
-            else slide_chain<T, false>(p1, p2, pd, 0, d, n_el, sum);
+            if (slot == 0) slide_chain_ring<T, true>(sX, RX, i1, i2, pd, RD, d, n_el, sum);
+            else slide_chain_ring<T, false>(sX, RX, i1, i2, pd, 0, d, n_el, sum);
           }
         } else {
           const int chains = a.chains;
@@ -876,8 +902,7 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
             const int slot = k == 0 ? slot_d0 : slot_d1;
             const int L = a.seg_len[k];
             const int base1 = wrap_up(sxn + a.cx1[k], RX);
-            const T* const x1 = sX + base1;
-            const T* const x2 = sX + wrap_up(sxn + a.cx2[k], RX);
+            const int base2 = wrap_up(sxn + a.cx2[k], RX);
             T* const dnew = sD + slot * tile;
             for (int u = dt; u < chains * a.n_seg[k]; u += ND) {
               const int s = u / chains, c = u - s * chains;
@@ -891,8 +916,10 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
                 for (int q = 1; q <= a.m[k]; ++q) sum += sX[wrap_both(base1 + e - q * d, RX)];
               }
               const int n_el = (min(tile, e + L * d) - e + d - 1) / d;
-              if (slot == 0) slide_chain<T, true>(x1 + e, x2 + e, dnew + e, RD, d, n_el, sum);
-              else slide_chain<T, false>(x1 + e, x2 + e, dnew + e, 0, d, n_el, sum);
+              if (slot == 0)
+                slide_chain_ring<T, true>(sX, RX, base1 + e, base2 + e, dnew + e, RD, d, n_el, sum);
+              else
+                slide_chain_ring<T, false>(sX, RX, base1 + e, base2 + e, dnew + e, 0, d, n_el, sum);
             }
           }
         }
@@ -949,10 +976,21 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
 #pragma unroll
             for (int r = 0; r < RU; ++r) acc[r] += p[r * NG];
           };
-          auto sub_term = [&](int off) {
-            const T* p = reinterpret_cast<const T*>(lane + off);
+          // X-ring terms (single taps, the centre sample): no mirror chunk, wrap per lane
+          const int x_end = 128 + a.tab_bytes + RX * ES, x_ring = RX * ES;
+          auto load_x = [&](int off, T (&v)[RU]) {
 #pragma unroll
-            for (int r = 0; r < RU; ++r) acc[r] -= p[r * NG];
+            for (int r = 0; r < RU; ++r) {
+              int pos = off + (i0 + r * NG) * ES;
+              if (pos >= x_end) pos -= x_ring;
+              v[r] = *reinterpret_cast<const T*>(smem_raw + pos);
+            }
+          };
+          auto add_x = [&](int off, T sign) {
+            T v[RU];
+            load_x(off, v);
+#pragma unroll
+            for (int r = 0; r < RU; ++r) acc[r] = fma(sign, v[r], acc[r]);
           };
           int x_centre;
           if (a.small_plan) {
@@ -982,8 +1020,8 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
             const int xo[3] = {ox.y, ox.z, ox.w};
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
-              if (t < n_plus) add_term(xo[t]);
-              else if (t < n_plus + n_minus) sub_term(xo[t]);
+              if (t < n_plus) add_x(xo[t], T(1));
+              else if (t < n_plus + n_minus) add_x(xo[t], T(-1));
             }
           } else {
             x_centre = rowx[0];
@@ -1004,23 +1042,24 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
 #pragma unroll 1
             for (; t < n_box1; ++t) add_term(row1[t]);
 #pragma unroll 1
-            for (t = 1; t <= n_plus; ++t) add_term(rowx[t]);
+            for (t = 1; t <= n_plus; ++t) add_x(rowx[t], T(1));
 #pragma unroll 1
-            for (t = 1 + n_plus; t <= n_plus + n_minus; ++t) sub_term(rowx[t]);
+            for (t = 1 + n_plus; t <= n_plus + n_minus; ++t) add_x(rowx[t], T(-1));
           }
-          const T* const xc = reinterpret_cast<const T*>(lane + x_centre);
+          T xc[RU];
+          load_x(x_centre, xc);
           T* const og = orow + cur + i0;
           if (interior && all_out) {
 #pragma unroll
             for (int r = 0; r < RU; ++r) {
-              const T x0 = xc[r * NG];
+              const T x0 = xc[r];
               og[r * NG] = x0 - (acc[r] + centre * x0) * inv_n;
             }
           } else {
 #pragma unroll
             for (int r = 0; r < RU; ++r) {
               const int64_t g = cur + i0 + r * NG;
-              const T x0 = xc[r * NG];
+              const T x0 = xc[r];
               const T sum = acc[r] + centre * x0;
               const int n_in =
                   interior ? a.n_taps : taps_in_range(a.taps, a.n_taps, g, a.n_total);
@@ -1075,7 +1114,8 @@ int launch_strip(const FilterPlanHeader* hdr, const int32_t* h_terms, const int3
   // kernel with a big tile (which amortises its two barriers per step) comes next, then
   // smaller tiles for wide tap windows.
   const StripTuning shapes[] = {
-      {1, 256, 256, 6, 1536, 2, 1}, {1, 512, 256, 2, 1024, 3, 1}, {0, 512, 0, 4, 2048, 3, 1},
+      {1, 512, 512, 4, 2048, 1, 1}, {1, 256, 256, 6, 1536, 2, 1}, {1, 512, 256, 2, 1024, 3, 1},
+      {0, 512, 0, 4, 2048, 3, 1},
       {1, 256, 256, 2, 512, 3, 1},  {0, 256, 0, 3, 768, 2, 2},    {0, 512, 0, 2, 1024, 4, 1},
       {0, 256, 0, 2, 512, 4, 2},    {0, 256, 0, 2, 512, 3, 1},    {0, 256, 0, 1, 256, 4, 1}};
   StripTuning pick{0, 0, 0, 0, 0, 0, 0};
@@ -1100,7 +1140,7 @@ int launch_strip(const FilterPlanHeader* hdr, const int32_t* h_terms, const int3
     const int64_t h_back = ceil_div(int64_t(f.w_hi) + a.d, tile);
     const int64_t h_fwd = ceil_div(-int64_t(f.w_lo), tile);
     const int64_t nq_x = h_back + h_fwd + extra + s.prefetch;
-    int64_t elems = (nq_x + 1) * tile;
+    int64_t elems = (nq_x + (s.pipe ? 0 : 1)) * tile;  // the pipelined kernel's X ring has no mirror
     int64_t tab_ints = nq_x * round4(1 + hdr->n_plus + hdr->n_minus) + 8;
     for (int k = 0; k < kMaxBoxKinds; ++k) {
       const int64_t reach = max64(int64_t(hdr->a_max[k]) - hdr->a_min[k], a.d);
@@ -1190,6 +1230,7 @@ int launch_strip(const FilterPlanHeader* hdr, const int32_t* h_terms, const int3
     PARRM_PIPE_SHAPE(256, 128, 2) PARRM_PIPE_SHAPE(256, 128, 4) PARRM_PIPE_SHAPE(512, 128, 2)
     PARRM_PIPE_SHAPE(768, 256, 2) PARRM_PIPE_SHAPE(384, 256, 4) PARRM_PIPE_SHAPE(768, 128, 2)
     PARRM_PIPE_SHAPE(256, 256, 6) PARRM_PIPE_SHAPE(384, 128, 4) PARRM_PIPE_SHAPE(384, 384, 4)
+    PARRM_PIPE_SHAPE(256, 256, 8) PARRM_PIPE_SHAPE(512, 512, 4)
 #undef PARRM_PIPE_SHAPE
   } else {
 #define PARRM_STRIP_SHAPE(NT_, RU_) \

@@ -59,8 +59,8 @@ def run(label, strategy, env):
 run("gather", _native.PLAN_GATHER, {})
 run("auto-default", _native.PLAN_AUTO, {})
 for pipe, threads, slide, ru, tile, pre, ctas in [
-    (1, 256, 256, 6, 1536, 2, 1), (1, 384, 256, 4, 1536, 2, 1), (1, 512, 256, 3, 1536, 2, 1),
-    (1, 256, 256, 4, 1024, 3, 1), (1, 512, 256, 2, 1024, 3, 1), (1, 768, 256, 2, 1536, 2, 1),
+    (1, 256, 256, 6, 1536, 2, 1), (1, 256, 256, 6, 1536, 1, 1), (1, 384, 256, 4, 1536, 2, 1),
+    (1, 256, 256, 8, 2048, 1, 1), (1, 512, 256, 4, 2048, 1, 1), (1, 512, 512, 4, 2048, 1, 1),
 ]:
     run(f"pipe{pipe} t{threads}+{slide} ru{ru} tile{tile} pre{pre} ctas{ctas}", _native.PLAN_AUTO,
         {"PARRM_FILTER_TILE": tile, "PARRM_FILTER_THREADS": threads, "PARRM_FILTER_RU": ru,
