@@ -19,3 +19,13 @@ periods = 2000 / 130 * (1 + np.linspace(-3e-3, 3e-3, n_cand))
 for _ in range(int(os.environ.get("PROF_PASSES", "4"))):
     err = engine.evaluate(tile, periods, 20, 1.0, n_chans)
 print("best", periods[err.argmin()], err.min())
+
+if os.environ.get("PROF_TABLE") == "1":  # kernel durations without ncu, for cross-checking
+    from torch.profiler import ProfilerActivity, profile
+
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        err = engine.evaluate(tile, periods, 20, 1.0, n_chans)
+        torch.cuda.synchronize()
+    for e in prof.key_averages():
+        if e.device_time_total > 0:
+            print(f"  {e.key[:70]:70s} x{e.count} {e.device_time_total / e.count:.1f} us each")

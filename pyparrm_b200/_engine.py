@@ -290,14 +290,15 @@ class DeviceEngine:
                 d_per = periods.to(device=self.device, dtype=t.float64).contiguous()
             n_periods = int(d_per.shape[0])
             d_err = t.empty(n_periods, dtype=t.float64, device=self.device)
-            per_cand = max(
-                1, lib.parrm_eval_workspace_bytes(tile.n_chans, tile.n_indices, 1, bandwidth)
-            )
-            batch = max(1, min(n_periods, _EVAL_WS_LIMIT // per_cand))
-            # workspace size is not linear in the batch (sample splits shrink as it grows)
+            # One launch for the whole grid when its workspace fits (the sample splits, and with
+            # them the workspace per candidate, shrink as the batch grows); otherwise halve.
+            batch = n_periods
+            while batch > 1 and lib.parrm_eval_workspace_bytes(
+                    tile.n_chans, tile.n_indices, batch, bandwidth) > _EVAL_WS_LIMIT:
+                batch = -(-batch // 2)
             ws_bytes = max(
                 lib.parrm_eval_workspace_bytes(tile.n_chans, tile.n_indices, b, bandwidth)
-                for b in {batch, min(batch, n_periods % batch or batch)}
+                for b in {batch, n_periods % batch or batch}
             )
             if self._eval_ws is None or self._eval_ws.numel() < ws_bytes:
                 self._eval_ws = self._empty(ws_bytes, t.uint8)

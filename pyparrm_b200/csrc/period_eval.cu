@@ -20,6 +20,8 @@
 // candidate (few candidates, e.g. Nelder-Mead steps); partials are combined in a fixed order.
 // Kernel 2 (solve) assembles the Gram matrix, factorises it with partial pivoting (zero pivot
 // -> +inf, the reference's LinAlgError path), solves all channels and reduces the objective.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace parrm {
@@ -61,6 +63,31 @@ __device__ __forceinline__ void cmul(double& c, double& s, double c2, double s2)
   s = ns;
 }
 
+// sin and cos of a phase angle a = (index + 1) * 2 pi / period (parrm.py:619).  The angles reach
+// ~5e5 rad on a ten-minute recording, far beyond the threshold (|a| > 105615) above which
+// CUDA's sincos() takes its Payne-Hanek slow path through local memory -- measured as the
+// bottleneck of the whole evaluator.  For |a| < 1e9 a three-term Cody-Waite reduction with
+// FMAs is exact to ~1e-16 rad: q = rint(a * 2/pi) < 2^30, each fma(-q, C_i, r) rounds once, and
+// C1 + C2 + C3 = pi/2 to 5.6e-50.  The reduced argument |r| <= pi/4 then takes sincos()'s fast
+// path and the quadrant is applied by hand.
+__device__ __forceinline__ void sincos_phase(double a, double* sn, double* cs) {
+  if (!(fabs(a) < 1.0e9)) {
+    sincos(a, sn, cs);
+    return;
+  }
+  const double q = rint(a * 0.6366197723675814);
+  double r = fma(-q, 1.5707963267948966, a);
+  r = fma(-q, 6.123233995736766e-17, r);
+  r = fma(-q, -1.4973849048591698e-33, r);
+  double s, c;
+  sincos(r, &s, &c);
+  const int quadrant = int(static_cast<long long>(q) & 3);
+  const double s1 = (quadrant & 1) ? c : s;
+  const double c1 = (quadrant & 1) ? s : c;
+  *sn = (quadrant & 2) ? -s1 : s1;
+  *cs = ((quadrant + 1) & 2) ? -c1 : c1;
+}
+
 // (c, s) = (c1 + i s1)^n by binary powering
 __device__ __forceinline__ void cpow(double c1, double s1, int n, double& c, double& s) {
   c = 1.0;
@@ -83,6 +110,11 @@ __device__ __forceinline__ int y_slot(int k, int c) {
 // 8-byte asynchronous global -> shared copy (LDGSTS); src_bytes = 0 writes zeros.
 __device__ __forceinline__ void cp_async8(double* dst_smem, const double* src, int src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst_smem)),
+               "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async16(double* dst_smem, const double* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)),
                "l"(src), "r"(src_bytes)
                : "memory");
 }
@@ -158,7 +190,7 @@ eval_accumulate_kernel(const double* __restrict__ y, const int64_t* __restrict__
       double2 cs = make_double2(0.0, 0.0);
       if (n < n_end) {
         const double angle = double(indices[n] + 1) * delta;
-        sincos(angle, &cs.y, &cs.x);
+        sincos_phase(angle, &cs.y, &cs.x);
       }
       s_cs[tid] = cs;
     }
@@ -261,6 +293,251 @@ eval_accumulate_kernel(const double* __restrict__ y, const int64_t* __restrict__
       if (j < h && m <= two_bw) {
         tp[m - 1] = s_red[(2 * g) * 2 * H + j] + s_red[(2 * g + 1) * 2 * H + j];
         tp[two_bw + m - 1] = s_red[(2 * g) * 2 * H + H + j] + s_red[(2 * g + 1) * 2 * H + H + j];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp-specialised form of the accumulate kernel (default).  Measured on the two-phase kernel
+// above: the FP64 pipe is 44 % busy, more than half of the samples are FMA warps waiting for
+// their shared-memory operands, and generation, staging and the FMA tiles take turns behind
+// block barriers.  Here 4 generator warps produce tile t + 1 (accurate sincos, harmonic
+// recurrence, W rows, cp.async of the Y rows, harmonic sums in their registers) while 8 FMA
+// warps consume tile t with their operands double-buffered in registers; two mbarrier pairs
+// (full / empty) hand the two shared-memory stages over, so the FMA warps never wait for a
+// block barrier.  Same arithmetic, same workspace layout, one CTA of 384 threads per SM.
+constexpr int kFmaThreads = 256;
+constexpr int kGenThreads = 256;   // 64 sample lanes x 4 harmonic groups
+constexpr int kWsThreads = kFmaThreads + kGenThreads;
+constexpr int kGenGroups = kGenThreads / kKT;
+constexpr int kGenH = (2 * PARRM_MAX_BANDWIDTH + kGenGroups - 1) / kGenGroups;  // harmonics per group
+constexpr int kGenBatch = kGenThreads;  // samples per sincos batch (one per generator thread)
+// Shared-memory tiles of the tensor-core path.  W is stored transposed, [row][sample], Y as
+// [sample][channel]; both with a row stride = 4 (mod 16) doubles, which makes the m8n8k4 fragment
+// loads (lane -> (l % 4, l / 4)) and the generator's stores (lane -> sample) conflict-free.
+constexpr int kWtStride = 68;   // >= kKT
+constexpr int kYStride = 68;    // >= kChanTile
+constexpr int kWtTile = kRowsPad * kWtStride;
+constexpr int kYTile = kKT * kYStride;
+
+__global__ void __launch_bounds__(kWsThreads, 1)
+eval_accumulate_ws_kernel(const double* __restrict__ y, const int64_t* __restrict__ indices,
+                          const double* __restrict__ periods, double* __restrict__ ws,
+                          const EvalShape sh) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);           // [2]
+  uint64_t* empty = full + 2;                                        // [2]
+  double2* s_cs = reinterpret_cast<double2*>(smem_raw + 64);        // [kGenBatch] (cos, sin)
+  double* s_w = reinterpret_cast<double*>(smem_raw + 64 + kGenBatch * 16);  // 2 x [kRowsPad][kWtStride]
+  double* s_y = s_w + 2 * kWtTile;                                  // 2 x [kKT][kYStride]
+  double* s_red = s_y + 2 * kYTile;                                 // [8 warps][2 * kGenH]
+
+  const int tid = threadIdx.x;
+  const int64_t cand = blockIdx.x;
+  const int split = blockIdx.y;
+  const int ctile = blockIdx.z;
+  const int bw = sh.bandwidth, two_bw = 2 * bw;
+  const int n_rows = sh.n_rows;
+  const int64_t n_begin = int64_t(split) * sh.split_len;
+  const int64_t n_end = min(n_begin + sh.split_len, sh.n_indices);
+  const int chan0 = ctile * kChanTile;
+  const int n_chan_here = int(min64(kChanTile, sh.n_chans - chan0));
+  const int n_tiles = n_end > n_begin ? int((n_end - n_begin + kKT - 1) / kKT) : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kFmaThreads / 32);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (tid >= kFmaThreads) {
+    // ------------------------------- generator warps -------------------------------
+    const int gt = tid - kFmaThreads;
+    const int gi = gt & (kKT - 1), gg = gt / kKT;  // sample lane, harmonic group gg*h+1 .. gg*h+h
+    const int h = (two_bw + kGenGroups - 1) / kGenGroups;
+    const int m0 = gg * h;
+    const bool pair_copies = (sh.ld_y % 2 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    const double delta = 6.283185307179586 / periods[cand];  // 2*pi/period (parrm.py:619)
+    double sum_c[kGenH], sum_s[kGenH];
+#pragma unroll
+    for (int j = 0; j < kGenH; ++j) sum_c[j] = sum_s[j] = 0.0;
+    uint32_t empty_phase = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int s = t & 1;
+      const int64_t n_tile = n_begin + int64_t(t) * kKT;
+      if (t >= 2) {
+        mbar_wait(&empty[s], (empty_phase >> s) & 1u);
+        empty_phase ^= 1u << s;
+      }
+      // Y rows of this tile: asynchronous copies, waited for before the hand-over.  A thread
+      // keeps its channel(s) and walks the samples, so the address arithmetic is two adds.
+      {
+        double* dst = s_y + s * kYTile;
+        if (pair_copies) {
+          const int c = (gt & 31) * 2, k0 = gt >> 5;  // channel pair, first sample; 8 samples apart
+          const bool c_ok = c < n_chan_here;          // n_chans even whenever ld_y is used pairwise
+          for (int k = k0; k < kKT; k += kGenThreads / 32) {
+            const int64_t n = n_tile + k;
+            const bool ok = n < n_end && c_ok;
+            const int bytes = !ok ? 0 : (c + 1 < n_chan_here ? 16 : 8);
+            cp_async16(dst + k * kYStride + c, ok ? y + n * sh.ld_y + chan0 + c : y, bytes);
+          }
+        } else {
+          const int c = gt & 63, k0 = gt >> 6;
+          for (int k = k0; k < kKT; k += kGenThreads / 64) {
+            const int64_t n = n_tile + k;
+            const bool ok = n < n_end && c < n_chan_here;
+            cp_async8(dst + k * kYStride + c, ok ? y + n * sh.ld_y + chan0 + c : y, ok ? 8 : 0);
+          }
+        }
+        cp_async_commit();
+      }
+      if ((t % (kGenBatch / kKT)) == 0) {
+        // one accurate sincos per sample for the coming tiles; invalid lanes hold (0, 0)
+        const int64_t n = n_tile + gt;
+        double2 cs = make_double2(0.0, 0.0);
+        if (n < n_end) {
+          const double angle = double(indices[n] + 1) * delta;
+          sincos_phase(angle, &cs.y, &cs.x);
+        }
+        s_cs[gt] = cs;
+        named_bar_sync(1, kGenThreads);
+      }
+      {
+        const bool live = n_tile + gi < n_end;
+        const double2 cs1 = s_cs[(t % (kGenBatch / kKT)) * kKT + gi];
+        double c, sn;
+        cpow(cs1.x, cs1.y, m0, c, sn);
+        double* wcol = s_w + s * kWtTile + gi;  // wcol[row * kWtStride] = W[sample gi][row]
+        if (gg == 0) wcol[0] = live ? 1.0 : 0.0;
+        if (gg == kGenGroups - 1)
+          for (int r = n_rows; r < kRowsPad; ++r) wcol[r * kWtStride] = 0.0;  // padding rows
+#pragma unroll
+        for (int j = 0; j < kGenH; ++j) {
+          if (j >= h) break;  // uniform
+          cmul(c, sn, cs1.x, cs1.y);
+          const int m = m0 + j + 1;
+          if (m <= two_bw && live) {
+            sum_c[j] += c;
+            sum_s[j] += sn;
+          }
+          if (m <= bw) {  // columns 2m-1 = sin, 2m = cos (parrm.py:622-623)
+            wcol[(2 * m - 1) * kWtStride] = live ? sn : 0.0;
+            wcol[(2 * m) * kWtStride] = live ? c : 0.0;
+          }
+        }
+      }
+      cp_async_wait<0>();
+      named_bar_sync(1, kGenThreads);  // W rows and Y rows of every generator thread are in place
+      if (gt == 0) mbar_arrive(&full[s]);
+    }
+    for (int t = max(n_tiles - 2, 0); t < n_tiles; ++t) {  // consume the last two releases
+      const int s = t & 1;
+      mbar_wait(&empty[s], (empty_phase >> s) & 1u);
+      empty_phase ^= 1u << s;
+    }
+    // harmonic sums: reduce the 64 sample lanes of each group (channel tile 0 only)
+    if (ctile == 0) {
+      const int warp = gt >> 5, lane = gt & 31;
+#pragma unroll
+      for (int j = 0; j < kGenH; ++j) {
+        const double c = warp_sum(sum_c[j]);
+        const double sn = warp_sum(sum_s[j]);
+        if (lane == 0) {
+          s_red[warp * 2 * kGenH + j] = c;
+          s_red[warp * 2 * kGenH + kGenH + j] = sn;
+        }
+      }
+      named_bar_sync(1, kGenThreads);
+      double* tp = ws + sh.t_offset + cand * sh.t_stride_period + int64_t(split) * sh.t_stride_split;
+      // kKT / 32 = 2 warps per group: warps 2g and 2g + 1
+      for (int e = gt; e < kGenGroups * kGenH; e += kGenThreads) {
+        const int g = e / kGenH, j = e % kGenH;
+        const int m = g * h + j + 1;
+        if (j < h && m <= two_bw) {
+          tp[m - 1] = s_red[(2 * g) * 2 * kGenH + j] + s_red[(2 * g + 1) * 2 * kGenH + j];
+          tp[two_bw + m - 1] =
+              s_red[(2 * g) * 2 * kGenH + kGenH + j] + s_red[(2 * g + 1) * 2 * kGenH + kGenH + j];
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------------------------- FMA warps ----------------------------------
+  // B += W' Y on the FP64 tensor cores (mma.sync m8n8k4, SASS DMMA).  Measured here: DMMA and
+  // vector DFMA have the same peak (37 TFLOP/s) on B200, but the register-tiled DFMA loop
+  // stops at ~40 % of it (three distinct 64-bit register operands per FMA), while one DMMA
+  // performs 256 FMAs from one double per lane.  Warp (kh, nq): samples kh*32..+32 of the tile,
+  // channels 16 nq..+16, all row blocks of 8.
+  const int warp = tid >> 5, l = tid & 31;
+  const int kh = warp >> 2, nq = warp & 3;
+  const int n_mb = (n_rows + 7) >> 3;  // row blocks in use (<= 6)
+  double acc[6][2][2];
+#pragma unroll
+  for (int mb = 0; mb < 6; ++mb)
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+  uint32_t full_phase = 0;
+  for (int t = 0; t < n_tiles; ++t) {
+    const int s = t & 1;
+    mbar_wait(&full[s], (full_phase >> s) & 1u);
+    full_phase ^= 1u << s;
+    // fragment addresses: A[m][k] = W[k][m] -> lane (m = l / 4, k = l % 4); B[k][n] -> (k = l % 4, n = l / 4)
+    const double* wa = s_w + s * kWtTile + (l >> 2) * kWtStride + kh * (kKT / 2) + (l & 3);
+    const double* yb = s_y + s * kYTile + (kh * (kKT / 2) + (l & 3)) * kYStride + nq * 16 + (l >> 2);
+    double a_cur[6], b_cur[2];
+#pragma unroll
+    for (int mb = 0; mb < 6; ++mb) a_cur[mb] = mb < n_mb ? wa[mb * 8 * kWtStride] : 0.0;
+    b_cur[0] = yb[0];
+    b_cur[1] = yb[8];
+#pragma unroll 2
+    for (int step = 0; step < kKT / 8; ++step) {  // 8 k4-steps per K-half
+      double a_nxt[6], b_nxt[2];
+      const bool more = step + 1 < kKT / 8;
+#pragma unroll
+      for (int mb = 0; mb < 6; ++mb)
+        a_nxt[mb] = (more && mb < n_mb) ? wa[mb * 8 * kWtStride + (step + 1) * 4] : 0.0;
+      b_nxt[0] = more ? yb[(step + 1) * 4 * kYStride] : 0.0;
+      b_nxt[1] = more ? yb[(step + 1) * 4 * kYStride + 8] : 0.0;
+#pragma unroll
+      for (int mb = 0; mb < 6; ++mb) {
+        if (mb < n_mb) {
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb)
+            asm volatile(
+                "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                : "+d"(acc[mb][nb][0]), "+d"(acc[mb][nb][1])
+                : "d"(a_cur[mb]), "d"(b_cur[nb]));
+        }
+      }
+#pragma unroll
+      for (int mb = 0; mb < 6; ++mb) a_cur[mb] = a_nxt[mb];
+      b_cur[0] = b_nxt[0];
+      b_cur[1] = b_nxt[1];
+    }
+    __syncwarp();
+    if (l == 0) mbar_arrive(&empty[s]);
+  }
+  // ---- write the B partial of this (candidate, split, K-half): C fragment lane (row l / 4,
+  // channels 2 (l % 4), +1) ----
+  {
+    double* bp = ws + cand * sh.b_stride_period + (int64_t(split) * 2 + kh) * sh.b_stride_split;
+#pragma unroll
+    for (int mb = 0; mb < 6; ++mb) {
+      const int row = mb * 8 + (l >> 2);
+      if (row < n_rows) {
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int ch = nq * 16 + nb * 8 + 2 * (l & 3) + j;
+            if (ch < n_chan_here) bp[int64_t(row) * sh.n_chans + chan0 + ch] = acc[mb][nb][j];
+          }
       }
     }
   }
@@ -549,11 +826,20 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
   cudaStream_t s = as_stream(stream);
   double* ws = static_cast<double*>(d_workspace);
   dim3 grid((unsigned)n_periods, (unsigned)sh.n_splits, (unsigned)sh.n_chan_tiles);
-  const size_t smem =
-      size_t(kSuper * 16 + (kKT * kRowStride + 2 * kKT * kChanTile + 8 * 2 * kHMax) * sizeof(double));
-  PARRM_CUDA_OK(cudaFuncSetAttribute(eval_accumulate_kernel,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  eval_accumulate_kernel<<<grid, kAccThreads, smem, s>>>(d_y, d_indices, d_periods, ws, sh);
+  const char* two_phase = getenv("PARRM_EVAL_TWO_PHASE");
+  if (two_phase && *two_phase == '1') {
+    const size_t smem = size_t(kSuper * 16 + (kKT * kRowStride + 2 * kKT * kChanTile + 8 * 2 * kHMax) *
+                                                 sizeof(double));
+    PARRM_CUDA_OK(cudaFuncSetAttribute(eval_accumulate_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    eval_accumulate_kernel<<<grid, kAccThreads, smem, s>>>(d_y, d_indices, d_periods, ws, sh);
+  } else {
+    const size_t smem =
+        size_t(64 + kGenBatch * 16 + (2 * kWtTile + 2 * kYTile + 8 * 2 * kGenH) * sizeof(double));
+    PARRM_CUDA_OK(cudaFuncSetAttribute(eval_accumulate_ws_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    eval_accumulate_ws_kernel<<<grid, kWsThreads, smem, s>>>(d_y, d_indices, d_periods, ws, sh);
+  }
   PARRM_LAUNCH_OK("eval_accumulate_kernel");
   const size_t solve_smem =
       size_t(kMaxRows * (2 * kGStride + 2 + 2 * kSolveThreads)) * sizeof(double);

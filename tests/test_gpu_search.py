@@ -187,3 +187,21 @@ def test_reference_suite_matrix(gpu_engine, n_chans, n_samples, search_portion):
     assert repr(parrm) == (
         f"PARRM object | Data: ({n_chans} channels x {n_samples} times) | Period: {parrm.period :.4f}")
     assert np.isfinite(parrm.period)
+
+
+def test_large_sample_indices(gpu_engine):
+    """Phase angles of a long recording (indices ~1e6, angles ~5e5 rad) go through the
+    evaluator's own argument reduction instead of sincos()'s slow path: check it against the
+    oracle there, for both the contiguous and the random-index branch."""
+    n_chans, n = 2, 1_200_000
+    data = make_recording(n_chans, n, 2000, 130, seed=21)
+    z = oracle.standardise(data, 3.0)
+    rng = np.random.default_rng(3)
+    per = 2000 / 130 * (1 + 3e-6)
+    periods = per * (1 + np.array([-2e-3, -1e-5, 0.0, 3e-6, 4e-4]))
+    for idx in (np.arange(1_100_000, 1_105_001),
+                np.unique(rng.integers(0, n - 60_002, 6000)) + 30_000):
+        (tile,) = gpu_engine.prepare_tiles(data, [idx], 3.0)
+        got = gpu_engine.evaluate(tile, periods, 20, 1.0, n_chans)
+        want = oracle.objective_many(periods, z, idx, 20, 1.0, n_chans, n_jobs=4)
+        compare_objective(got, want, "large indices", periods, idx, 20)
