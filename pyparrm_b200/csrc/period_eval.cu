@@ -312,7 +312,8 @@ constexpr int kGenThreads = 256;   // 64 sample lanes x 4 harmonic groups
 constexpr int kWsThreads = kFmaThreads + kGenThreads;
 constexpr int kGenGroups = kGenThreads / kKT;
 constexpr int kGenH = (2 * PARRM_MAX_BANDWIDTH + kGenGroups - 1) / kGenGroups;  // harmonics per group
-constexpr int kGenBatch = kGenThreads;  // samples per sincos batch (one per generator thread)
+constexpr int kTeamThreads = kGenThreads / 2;  // two generator teams produce alternate tiles
+constexpr int kWsStages = 3;
 // Shared-memory tiles of the tensor-core path.  W is stored transposed, [row][sample], Y as
 // [sample][channel]; both with a row stride = 4 (mod 16) doubles, which makes the m8n8k4 fragment
 // loads (lane -> (l % 4, l / 4)) and the generator's stores (lane -> sample) conflict-free.
@@ -326,12 +327,12 @@ eval_accumulate_ws_kernel(const double* __restrict__ y, const int64_t* __restric
                           const double* __restrict__ periods, double* __restrict__ ws,
                           const EvalShape sh) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);           // [2]
-  uint64_t* empty = full + 2;                                        // [2]
-  double2* s_cs = reinterpret_cast<double2*>(smem_raw + 64);        // [kGenBatch] (cos, sin)
-  double* s_w = reinterpret_cast<double*>(smem_raw + 64 + kGenBatch * 16);  // 2 x [kRowsPad][kWtStride]
-  double* s_y = s_w + 2 * kWtTile;                                  // 2 x [kKT][kYStride]
-  double* s_red = s_y + 2 * kYTile;                                 // [8 warps][2 * kGenH]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);           // [kWsStages]
+  uint64_t* empty = full + kWsStages;                                // [kWsStages]
+  double2* s_cs = reinterpret_cast<double2*>(smem_raw + 64);        // [2 teams][kTeamThreads] (cos, sin)
+  double* s_w = reinterpret_cast<double*>(smem_raw + 64 + kGenThreads * 16);  // stages x [kRowsPad][kWtStride]
+  double* s_y = s_w + kWsStages * kWtTile;                          // stages x [kKT][kYStride]
+  double* s_red = s_y + kWsStages * kYTile;                         // [8 warps][2 * kGenH]
 
   const int tid = threadIdx.x;
   const int64_t cand = blockIdx.x;
@@ -346,49 +347,54 @@ eval_accumulate_ws_kernel(const double* __restrict__ y, const int64_t* __restric
   const int n_tiles = n_end > n_begin ? int((n_end - n_begin + kKT - 1) / kKT) : 0;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kWsStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], kFmaThreads / 32);
     }
     fence_mbar_init();
   }
   __syncthreads();
+  // Tile t lives in stage t % 3; its full / empty barriers complete once per use of the stage,
+  // so the parity a waiter needs follows from t alone (no per-thread phase state).
 
   if (tid >= kFmaThreads) {
     // ------------------------------- generator warps -------------------------------
+    // Two teams of 4 warps produce alternate tiles (team = t & 1), each into its own stage, so
+    // the generator's latency -- dependent FP64 chains that queue behind the tensor-core work
+    // on the same pipe -- has two tile times to hide in.  A team thread carries two samples
+    // (gi, gi + 32) of one harmonic group as independent chains.
     const int gt = tid - kFmaThreads;
-    const int gi = gt & (kKT - 1), gg = gt / kKT;  // sample lane, harmonic group gg*h+1 .. gg*h+h
-    const int h = (two_bw + kGenGroups - 1) / kGenGroups;
-    const int m0 = gg * h;
-    const bool pair_copies = (sh.ld_y % 2 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    const int team = gt / kTeamThreads, tt = gt % kTeamThreads;
+    // harmonic group gg takes m = gg + 1, gg + 5, gg + 9, ...: seeds z^(gg+1) cost <= 3 complex
+    // products and every further harmonic one product by z^4 (short dependent chains)
+    const int gi = tt & 31, gg = tt >> 5;
+    const int h = (two_bw - gg + kGenGroups - 1) / kGenGroups;  // harmonics of this group
     const double delta = 6.283185307179586 / periods[cand];  // 2*pi/period (parrm.py:619)
+    const bool pair_copies = (sh.ld_y % 2 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    double2* cs_team = s_cs + team * kTeamThreads;
     double sum_c[kGenH], sum_s[kGenH];
 #pragma unroll
     for (int j = 0; j < kGenH; ++j) sum_c[j] = sum_s[j] = 0.0;
-    uint32_t empty_phase = 0;
-    for (int t = 0; t < n_tiles; ++t) {
-      const int s = t & 1;
+    int i = 0;  // index of the tile among this team's tiles
+    for (int t = team; t < n_tiles; t += 2, ++i) {
+      const int s = t % kWsStages;
       const int64_t n_tile = n_begin + int64_t(t) * kKT;
-      if (t >= 2) {
-        mbar_wait(&empty[s], (empty_phase >> s) & 1u);
-        empty_phase ^= 1u << s;
-      }
-      // Y rows of this tile: asynchronous copies, waited for before the hand-over.  A thread
-      // keeps its channel(s) and walks the samples, so the address arithmetic is two adds.
+      if (t >= kWsStages) mbar_wait(&empty[s], uint32_t(t / kWsStages - 1) & 1u);
+      // Y rows of this tile: asynchronous copies, waited for before the hand-over
       {
         double* dst = s_y + s * kYTile;
         if (pair_copies) {
-          const int c = (gt & 31) * 2, k0 = gt >> 5;  // channel pair, first sample; 8 samples apart
-          const bool c_ok = c < n_chan_here;          // n_chans even whenever ld_y is used pairwise
-          for (int k = k0; k < kKT; k += kGenThreads / 32) {
+          const int c = (tt & 31) * 2, k0 = tt >> 5;  // channel pair, first sample; 4 samples apart
+          const bool c_ok = c < n_chan_here;
+          for (int k = k0; k < kKT; k += kTeamThreads / 32) {
             const int64_t n = n_tile + k;
             const bool ok = n < n_end && c_ok;
             const int bytes = !ok ? 0 : (c + 1 < n_chan_here ? 16 : 8);
             cp_async16(dst + k * kYStride + c, ok ? y + n * sh.ld_y + chan0 + c : y, bytes);
           }
         } else {
-          const int c = gt & 63, k0 = gt >> 6;
-          for (int k = k0; k < kKT; k += kGenThreads / 64) {
+          const int c = tt & 63, k0 = tt >> 6;
+          for (int k = k0; k < kKT; k += kTeamThreads / 64) {
             const int64_t n = n_tile + k;
             const bool ok = n < n_end && c < n_chan_here;
             cp_async8(dst + k * kYStride + c, ok ? y + n * sh.ld_y + chan0 + c : y, ok ? 8 : 0);
@@ -396,53 +402,76 @@ eval_accumulate_ws_kernel(const double* __restrict__ y, const int64_t* __restric
         }
         cp_async_commit();
       }
-      if ((t % (kGenBatch / kKT)) == 0) {
-        // one accurate sincos per sample for the coming tiles; invalid lanes hold (0, 0)
-        const int64_t n = n_tile + gt;
+      if ((i & 1) == 0) {
+        // one accurate sincos per sample for this tile and the team's next one (t + 2);
+        // invalid lanes hold (0, 0)
+        const int64_t n = n_tile + int64_t(tt >> 6) * 2 * kKT + (tt & 63);
         double2 cs = make_double2(0.0, 0.0);
         if (n < n_end) {
           const double angle = double(indices[n] + 1) * delta;
           sincos_phase(angle, &cs.y, &cs.x);
         }
-        s_cs[gt] = cs;
-        named_bar_sync(1, kGenThreads);
+        cs_team[tt] = cs;
+        named_bar_sync(1 + team, kTeamThreads);
       }
       {
-        const bool live = n_tile + gi < n_end;
-        const double2 cs1 = s_cs[(t % (kGenBatch / kKT)) * kKT + gi];
-        double c, sn;
-        cpow(cs1.x, cs1.y, m0, c, sn);
-        double* wcol = s_w + s * kWtTile + gi;  // wcol[row * kWtStride] = W[sample gi][row]
-        if (gg == 0) wcol[0] = live ? 1.0 : 0.0;
+        const bool live_a = n_tile + gi < n_end, live_b = n_tile + gi + 32 < n_end;
+        const double2 za = cs_team[(i & 1) * kKT + gi], zb = cs_team[(i & 1) * kKT + gi + 32];
+        // z^2, z^4 and the seed z^(gg+1) of both samples
+        double a2c = za.x, a2s = za.y, b2c = zb.x, b2s = zb.y;
+        cmul(a2c, a2s, za.x, za.y);
+        cmul(b2c, b2s, zb.x, zb.y);
+        double a4c = a2c, a4s = a2s, b4c = b2c, b4s = b2s;
+        cmul(a4c, a4s, a2c, a2s);
+        cmul(b4c, b4s, b2c, b2s);
+        double ca = za.x, sa = za.y, cb = zb.x, sb = zb.y;  // gg == 0: z
+        if (gg == 1) {
+          ca = a2c; sa = a2s; cb = b2c; sb = b2s;
+        } else if (gg == 2) {
+          ca = a2c; sa = a2s; cb = b2c; sb = b2s;
+          cmul(ca, sa, za.x, za.y);
+          cmul(cb, sb, zb.x, zb.y);
+        } else if (gg == 3) {
+          ca = a4c; sa = a4s; cb = b4c; sb = b4s;
+        }
+        double* wcol = s_w + s * kWtTile + gi;  // wcol[row * kWtStride (+ 32)] = W[sample][row]
+        if (gg == 0) {
+          wcol[0] = live_a ? 1.0 : 0.0;
+          wcol[32] = live_b ? 1.0 : 0.0;
+        }
         if (gg == kGenGroups - 1)
-          for (int r = n_rows; r < kRowsPad; ++r) wcol[r * kWtStride] = 0.0;  // padding rows
+          for (int r = n_rows; r < kRowsPad; ++r) wcol[r * kWtStride] = wcol[r * kWtStride + 32] = 0.0;
 #pragma unroll
         for (int j = 0; j < kGenH; ++j) {
-          if (j >= h) break;  // uniform
-          cmul(c, sn, cs1.x, cs1.y);
-          const int m = m0 + j + 1;
-          if (m <= two_bw && live) {
-            sum_c[j] += c;
-            sum_s[j] += sn;
+          if (j >= h) break;  // uniform within a warp (one group per warp)
+          if (j > 0) {
+            cmul(ca, sa, a4c, a4s);
+            cmul(cb, sb, b4c, b4s);
+          }
+          const int m = gg + 1 + kGenGroups * j;  // <= two_bw by the choice of h
+          if (live_a) {
+            sum_c[j] += ca;
+            sum_s[j] += sa;
+          }
+          if (live_b) {
+            sum_c[j] += cb;
+            sum_s[j] += sb;
           }
           if (m <= bw) {  // columns 2m-1 = sin, 2m = cos (parrm.py:622-623)
-            wcol[(2 * m - 1) * kWtStride] = live ? sn : 0.0;
-            wcol[(2 * m) * kWtStride] = live ? c : 0.0;
+            wcol[(2 * m - 1) * kWtStride] = live_a ? sa : 0.0;
+            wcol[(2 * m) * kWtStride] = live_a ? ca : 0.0;
+            wcol[(2 * m - 1) * kWtStride + 32] = live_b ? sb : 0.0;
+            wcol[(2 * m) * kWtStride + 32] = live_b ? cb : 0.0;
           }
         }
       }
       cp_async_wait<0>();
-      named_bar_sync(1, kGenThreads);  // W rows and Y rows of every generator thread are in place
-      if (gt == 0) mbar_arrive(&full[s]);
+      named_bar_sync(1 + team, kTeamThreads);  // W and Y rows of every team thread are in place
+      if (tt == 0) mbar_arrive(&full[s]);
     }
-    for (int t = max(n_tiles - 2, 0); t < n_tiles; ++t) {  // consume the last two releases
-      const int s = t & 1;
-      mbar_wait(&empty[s], (empty_phase >> s) & 1u);
-      empty_phase ^= 1u << s;
-    }
-    // harmonic sums: reduce the 64 sample lanes of each group (channel tile 0 only)
+    // harmonic sums: reduce over the sample lanes and the two teams (channel tile 0 only)
     if (ctile == 0) {
-      const int warp = gt >> 5, lane = gt & 31;
+      const int warp = gt >> 5, lane = gt & 31;  // warp = team * 4 + group
 #pragma unroll
       for (int j = 0; j < kGenH; ++j) {
         const double c = warp_sum(sum_c[j]);
@@ -452,16 +481,14 @@ eval_accumulate_ws_kernel(const double* __restrict__ y, const int64_t* __restric
           s_red[warp * 2 * kGenH + kGenH + j] = sn;
         }
       }
-      named_bar_sync(1, kGenThreads);
+      named_bar_sync(3, kGenThreads);
       double* tp = ws + sh.t_offset + cand * sh.t_stride_period + int64_t(split) * sh.t_stride_split;
-      // kKT / 32 = 2 warps per group: warps 2g and 2g + 1
       for (int e = gt; e < kGenGroups * kGenH; e += kGenThreads) {
         const int g = e / kGenH, j = e % kGenH;
-        const int m = g * h + j + 1;
-        if (j < h && m <= two_bw) {
-          tp[m - 1] = s_red[(2 * g) * 2 * kGenH + j] + s_red[(2 * g + 1) * 2 * kGenH + j];
-          tp[two_bw + m - 1] =
-              s_red[(2 * g) * 2 * kGenH + kGenH + j] + s_red[(2 * g + 1) * 2 * kGenH + kGenH + j];
+        const int m = g + 1 + kGenGroups * j;  // harmonic j of group g
+        if (m <= two_bw) {
+          tp[m - 1] = s_red[g * 2 * kGenH + j] + s_red[(g + 4) * 2 * kGenH + j];
+          tp[two_bw + m - 1] = s_red[g * 2 * kGenH + kGenH + j] + s_red[(g + 4) * 2 * kGenH + kGenH + j];
         }
       }
     }
@@ -482,11 +509,9 @@ eval_accumulate_ws_kernel(const double* __restrict__ y, const int64_t* __restric
   for (int mb = 0; mb < 6; ++mb)
 #pragma unroll
     for (int nb = 0; nb < 2; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
-  uint32_t full_phase = 0;
   for (int t = 0; t < n_tiles; ++t) {
-    const int s = t & 1;
-    mbar_wait(&full[s], (full_phase >> s) & 1u);
-    full_phase ^= 1u << s;
+    const int s = t % kWsStages;
+    mbar_wait(&full[s], uint32_t(t / kWsStages) & 1u);
     // fragment addresses: A[m][k] = W[k][m] -> lane (m = l / 4, k = l % 4); B[k][n] -> (k = l % 4, n = l / 4)
     const double* wa = s_w + s * kWtTile + (l >> 2) * kWtStride + kh * (kKT / 2) + (l & 3);
     const double* yb = s_y + s * kYTile + (kh * (kKT / 2) + (l & 3)) * kYStride + nq * 16 + (l >> 2);
@@ -544,7 +569,9 @@ eval_accumulate_ws_kernel(const double* __restrict__ y, const int64_t* __restric
 }
 
 // ------------------------------------------------------------------------------------------
-constexpr int kSolveThreads = 128;
+constexpr int kSolveThreads = 64;   // one channel per thread in the substitution phase; small, so
+                                    // that three CTAs (M = 41) share an SM and hide each other's
+                                    // dependent shared-memory chains
 constexpr int kGStride = kMaxRows + 1;  // row stride of the Gram matrix
 
 __global__ void __launch_bounds__(kSolveThreads)
@@ -553,11 +580,11 @@ eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sums
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int M = sh.n_rows, bw = sh.bandwidth, two_bw = 2 * bw;
   double* s_g = reinterpret_cast<double*>(smem_raw);   // [M][kGStride] LU factors
-  double* s_g0 = s_g + kMaxRows * kGStride;   // [M][kGStride] Gram matrix, kept unfactored
-  double* s_hc = s_g0 + kMaxRows * kGStride;  // C_0..C_2bw
+  double* s_g0 = s_g + M * kGStride;          // [M][kGStride] Gram matrix, kept unfactored
+  double* s_hc = s_g0 + M * kGStride;         // C_0..C_2bw
   double* s_hs = s_hc + kMaxRows;             // S_0..S_2bw
   double* s_b = s_hs + kMaxRows;              // [M][kSolveThreads] right-hand sides
-  double* s_x = s_b + kMaxRows * kSolveThreads;  // [M][kSolveThreads] work / solution
+  double* s_x = s_b + M * kSolveThreads;      // [M][kSolveThreads] work / solution
   __shared__ int s_perm[kMaxRows];
   __shared__ int s_piv;
   __shared__ int s_singular;
@@ -834,15 +861,15 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     eval_accumulate_kernel<<<grid, kAccThreads, smem, s>>>(d_y, d_indices, d_periods, ws, sh);
   } else {
-    const size_t smem =
-        size_t(64 + kGenBatch * 16 + (2 * kWtTile + 2 * kYTile + 8 * 2 * kGenH) * sizeof(double));
+    const size_t smem = size_t(64 + kGenThreads * 16 +
+                               (kWsStages * (kWtTile + kYTile) + 8 * 2 * kGenH) * sizeof(double));
     PARRM_CUDA_OK(cudaFuncSetAttribute(eval_accumulate_ws_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     eval_accumulate_ws_kernel<<<grid, kWsThreads, smem, s>>>(d_y, d_indices, d_periods, ws, sh);
   }
   PARRM_LAUNCH_OK("eval_accumulate_kernel");
   const size_t solve_smem =
-      size_t(kMaxRows * (2 * kGStride + 2 + 2 * kSolveThreads)) * sizeof(double);
+      size_t(sh.n_rows * (2 * kGStride + 2 * kSolveThreads) + 2 * kMaxRows) * sizeof(double);
   PARRM_CUDA_OK(cudaFuncSetAttribute(eval_solve_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      int(solve_smem)));
