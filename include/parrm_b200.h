@@ -161,6 +161,11 @@ int parrm_filter_apply(const void* d_x, int64_t ld_x, int64_t x_t0, int64_t n_x,
                        const void* d_plan, const void* h_plan,
                        int dtype, void* stream);
 
+/* Element-wise precision conversion for the float32 storage mode of the filter (the recording
+ * crosses PCIe as float64, as the reference's API hands it over, parrm.py:866-875). */
+int parrm_convert_f64_to_f32(const double* d_src, float* d_dst, int64_t n, void* stream);
+int parrm_convert_f32_to_f64(const float* d_src, double* d_dst, int64_t n, void* stream);
+
 /* Measured FP64 FMA throughput helper for the roofline denominator of the evaluator
  * (bench.py): runs `iters` dependent-chain DFMA batches on every SM; reports flops issued. */
 int parrm_fp64_fma_burn(int64_t iters, double* d_sink, double* h_flops, void* stream);

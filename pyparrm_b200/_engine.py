@@ -497,11 +497,13 @@ class DeviceEngine:
                     self.s_run.wait_event(slot["ev_out"])  # previous result left d_out
                 d_in_ptr, d_out_ptr = slot["d_in"].data_ptr(), slot["d_out"].data_ptr()
                 if compute_f32:
-                    with t.cuda.stream(self.s_run):
-                        x64 = slot["d_in"][: n_c * n_x * 8].view(t.float64)
-                        x32 = x64.to(t.float32)
+                    with t.cuda.stream(self.s_run):  # allocations ordered on the compute stream
+                        x32 = t.empty(n_c * n_x, dtype=t.float32, device=self.device)
                         y32 = t.empty(n_c * n_o, dtype=t.float32, device=self.device)
-                        tf32[k] = (x32, y32)
+                    tf32[k] = (x32, y32)
+                    check(lib.parrm_convert_f64_to_f32(_vp(d_in_ptr), _vp(x32.data_ptr()),
+                                                       n_c * n_x, s_run), "parrm_convert_f64_to_f32")
+                    self.launches += 1
                     d_in_ptr, d_out_ptr = x32.data_ptr(), y32.data_ptr()
                 check(lib.parrm_filter_apply(
                     _vp(d_in_ptr), n_x, x0, n_x, _vp(d_out_ptr), n_o, t0, n_o, n_samples, n_c,
@@ -509,8 +511,10 @@ class DeviceEngine:
                     "parrm_filter_apply")
                 self.launches += 1
                 if compute_f32:
-                    with t.cuda.stream(self.s_run):
-                        slot["d_out"][: n_c * n_o * 8].view(t.float64).copy_(tf32[k][1])
+                    check(lib.parrm_convert_f32_to_f64(_vp(tf32[k][1].data_ptr()),
+                                                       _vp(slot["d_out"].data_ptr()), n_c * n_o,
+                                                       s_run), "parrm_convert_f32_to_f64")
+                    self.launches += 1
                 slot["ev_run"].record(self.s_run)
                 self.s_out.wait_event(slot["ev_run"])
                 if out_pinned:

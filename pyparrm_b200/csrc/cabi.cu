@@ -28,9 +28,37 @@ __global__ void __launch_bounds__(256) fp64_burn_kernel(int64_t iters, double* s
   if (s == 123.456) sink[0] = s;  // never true; keeps the chains alive
 }
 
+template <typename S, typename D>
+__global__ void __launch_bounds__(256) convert_kernel(const S* __restrict__ src,
+                                                      D* __restrict__ dst, int64_t n) {
+  for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < n; i += int64_t(gridDim.x) * 256)
+    dst[i] = static_cast<D>(src[i]);
+}
+
+template <typename S, typename D>
+int convert(const S* src, D* dst, int64_t n, void* stream, const char* name) {
+  if (n <= 0) return PARRM_OK;
+  if (src == nullptr || dst == nullptr) {
+    set_error("%s: null pointer", name);
+    return PARRM_ERR_INVALID_ARGUMENT;
+  }
+  const int64_t blocks = min64(ceil_div(n, 256), int64_t(kNumSMs) * 16);
+  convert_kernel<S, D><<<unsigned(blocks), 256, 0, as_stream(stream)>>>(src, dst, n);
+  PARRM_LAUNCH_OK(name);
+  return PARRM_OK;
+}
+
 }  // namespace parrm
 
 extern "C" {
+
+int parrm_convert_f64_to_f32(const double* d_src, float* d_dst, int64_t n, void* stream) {
+  return parrm::convert<double, float>(d_src, d_dst, n, stream, "parrm_convert_f64_to_f32");
+}
+
+int parrm_convert_f32_to_f64(const float* d_src, double* d_dst, int64_t n, void* stream) {
+  return parrm::convert<float, double>(d_src, d_dst, n, stream, "parrm_convert_f32_to_f64");
+}
 
 int parrm_abi_version(void) { return PARRM_B200_ABI_VERSION; }
 
