@@ -197,6 +197,7 @@ int launch_filter(const FilterArgs<T>& args_in, int64_t n_chans, cudaStream_t st
 // strip) -> gather  y = x - (sum of terms)/n_in  -> coalesced store.
 // ====================================================================================
 constexpr int kMaxPrefetch = 8;
+constexpr int kMaxStages = 4;
 
 template <typename T>
 struct StripArgs {
@@ -229,6 +230,7 @@ struct StripArgs {
   int32_t tab_stride_d0, tab_stride_d1, tab_stride_x;
   int32_t small_plan;                  // every table row fits the preloaded registers
   int32_t piece_steps;                 // pipelined kernel: chunks per piece (direct re-evaluation)
+  int32_t stages;                      // pipelined kernel: hand-over stages (slide runs stages-1 ahead)
   int32_t off[kMaxTerms];              // per-term ring offsets: (-(a - a_lo_k)) mod |D_k| for
                                        // boxes, (-w) mod |X| for single taps
 };
@@ -697,8 +699,8 @@ template <typename T, int NG, int ND, int RU>
 __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripArgs<T> a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem_raw);  // [kMaxPrefetch] TMA chunks
-  uint64_t* const full = bars + kMaxPrefetch;                    // [2]
-  uint64_t* const empty = full + 2;                              // [2]
+  uint64_t* const full = bars + kMaxPrefetch;                    // [kMaxStages]
+  uint64_t* const empty = full + kMaxStages;                     // [kMaxStages]
   int32_t* const tab = reinterpret_cast<int32_t*>(smem_raw + 128);
   constexpr int VEC = 16 / sizeof(T);
   constexpr int ES = int(sizeof(T));
@@ -723,11 +725,12 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
   const T centre = T(a.centre);
   const int n_box0 = a.n_box[0], n_box1 = a.nk > 1 ? a.n_box[1] : 0;
   const int n_plus = a.n_plus, n_minus = a.n_minus;
-  const int back0 = a.nq_d[0] - 2, back1 = a.nk > 1 ? a.nq_d[1] - 2 : 0;
+  const int K = a.stages;  // the slide may run K - 1 chunks ahead of the gather
+  const int back0 = a.nq_d[0] - K, back1 = a.nk > 1 ? a.nq_d[1] - K : 0;
 
   if (tid == 0) {
     for (int b = 0; b < kMaxPrefetch; ++b) mbar_init(&bars[b], 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&full[s], 1);         // one elected slide thread arrives
       mbar_init(&empty[s], NG / 32);  // one lane of every gather warp arrives
     }
@@ -759,8 +762,11 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
   }
   // phase parities; every thread keeps the ones its role waits on
   uint32_t tma_phase = 0, tma_bits = 0;  // slide threads
-  uint32_t full_phase = 0;               // gather threads: bit s = parity to wait for
-  uint32_t empty_phase = 0;              // slide threads
+  // Chunk hand-overs are numbered by a counter g that runs on through the pieces of this CTA:
+  // hand-over g uses barrier pair g % K and completes its (g / K)-th phase, so the parity a
+  // waiter needs follows from g alone.  Kept incrementally: stage = g % K, phase = (g / K) & 1.
+  int hand_stage = 0, hand_count = 0;
+  uint32_t hand_phase = 0;
 
   const int64_t F_begin = a.total_steps * int64_t(blockIdx.x) / int64_t(gridDim.x);
   const int64_t F_end = a.total_steps * int64_t(blockIdx.x + 1) / int64_t(gridDim.x);
@@ -863,11 +869,8 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
       long long ptick__ = clock64();
 #endif
       for (int n = 0; n < n_steps; ++n) {
-        if (n >= 2) {  // the gather of chunk n - 2 has released the slots written below
-          const int s = n & 1;
-          mbar_wait(&empty[s], (empty_phase >> s) & 1u);
-          empty_phase ^= 1u << s;
-        }
+        if (hand_count >= K)  // the gather K hand-overs back has released the slots written below
+          mbar_wait(&empty[hand_stage], hand_phase ^ 1u);
         PIPE_TICK(NG, 4);
         if (r_issue <= r_need_max) issue_chunk(r_issue, slot_issue, bar_issue, dt, ND);
         ++r_issue;
@@ -934,17 +937,16 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
         bar_wait = wrap_up(bar_wait + 1, P);
         PIPE_TICK(NG, 6);
         named_bar_sync(1, ND);  // every slide thread is done with chunk n (and any sync loads)
-        if (dt == 0) mbar_arrive(&full[n & 1]);
+        if (dt == 0) mbar_arrive(&full[hand_stage]);
+        ++hand_count;
+        if (++hand_stage == K) {
+          hand_stage = 0;
+          hand_phase ^= 1u;
+        }
         PIPE_TICK(NG, 7);
         slot_x = wrap_up(slot_x + 1, a.nq_x);
         slot_d0 = wrap_up(slot_d0 + 1, a.nq_d[0]);
         if (a.nk > 1) slot_d1 = wrap_up(slot_d1 + 1, a.nq_d[1]);
-      }
-      // consume the releases of the last two gathers so that the parities stay in step
-      for (int n = max(n_steps - 2, 0); n < n_steps; ++n) {
-        const int s = n & 1;
-        mbar_wait(&empty[s], (empty_phase >> s) & 1u);
-        empty_phase ^= 1u << s;
       }
     } else {
       // ------------------------------ gather warps ------------------------------
@@ -954,11 +956,7 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
       long long ptick__ = clock64();
 #endif
       for (int n = 0; n < n_steps; ++n, cur += tile) {
-        {
-          const int s = n & 1;
-          mbar_wait(&full[s], (full_phase >> s) & 1u);
-          full_phase ^= 1u << s;
-        }
+        mbar_wait(&full[hand_stage], hand_phase);
         PIPE_TICK(0, 0);
         const bool interior = (cur - a.w_hi >= 0) && (cur + tile - a.w_lo <= a.n_total);
         const bool all_out = (cur >= a.t0) && (cur + tile <= a.t0 + a.n_out);
@@ -1071,7 +1069,11 @@ __global__ void __launch_bounds__(NG + ND) filter_comb_pipe_kernel(const StripAr
 #endif
         PIPE_TICK(0, 1);
         __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&empty[n & 1]);
+        if ((tid & 31) == 0) mbar_arrive(&empty[hand_stage]);
+        if (++hand_stage == K) {
+          hand_stage = 0;
+          hand_phase ^= 1u;
+        }
         PIPE_TICK(0, 2);
         slot_x = wrap_up(slot_x + 1, a.nq_x);
         slot_d0 = wrap_up(slot_d0 + 1, a.nq_d[0]);
@@ -1086,6 +1088,7 @@ struct StripTuning {
   int threads;      // gather threads (all threads when pipe = 0)
   int slide;        // slide threads (pipe = 1)
   int ru, tile, prefetch, ctas_per_sm;
+  int stages;       // pipe = 1: hand-over stages (2 or 3); the slide runs stages - 1 chunks ahead
 };
 
 template <typename T>
@@ -1114,11 +1117,11 @@ int launch_strip(const FilterPlanHeader* hdr, const int32_t* h_terms, const int3
   // kernel with a big tile (which amortises its two barriers per step) comes next, then
   // smaller tiles for wide tap windows.
   const StripTuning shapes[] = {
-      {1, 512, 512, 4, 2048, 1, 1}, {1, 256, 256, 6, 1536, 2, 1}, {1, 512, 256, 2, 1024, 3, 1},
-      {0, 512, 0, 4, 2048, 3, 1},
-      {1, 256, 256, 2, 512, 3, 1},  {0, 256, 0, 3, 768, 2, 2},    {0, 512, 0, 2, 1024, 4, 1},
-      {0, 256, 0, 2, 512, 4, 2},    {0, 256, 0, 2, 512, 3, 1},    {0, 256, 0, 1, 256, 4, 1}};
-  StripTuning pick{0, 0, 0, 0, 0, 0, 0};
+      {1, 512, 512, 4, 2048, 1, 1, 2}, {1, 256, 256, 6, 1536, 2, 1, 2}, {1, 512, 256, 2, 1024, 3, 1, 2},
+      {0, 512, 0, 4, 2048, 3, 1, 1},   {1, 256, 256, 2, 512, 3, 1, 2},  {0, 256, 0, 3, 768, 2, 2, 1},
+      {0, 512, 0, 2, 1024, 4, 1, 1},   {0, 256, 0, 2, 512, 4, 2, 1},    {0, 256, 0, 2, 512, 3, 1, 1},
+      {0, 256, 0, 1, 256, 4, 1, 1}};
+  StripTuning pick{0, 0, 0, 0, 0, 0, 0, 0};
   size_t pick_smem = 0;
   const int forced_tile = env_int("PARRM_FILTER_TILE", 0);
   const int allow_pipe = env_int("PARRM_FILTER_PIPE", 1);
@@ -1132,11 +1135,13 @@ int launch_strip(const FilterPlanHeader* hdr, const int32_t* h_terms, const int3
       s.ru = env_int("PARRM_FILTER_RU", s.ru);
       s.prefetch = env_int("PARRM_FILTER_PREFETCH", s.prefetch);
       s.ctas_per_sm = env_int("PARRM_FILTER_CTAS", s.ctas_per_sm);
+      s.stages = env_int("PARRM_FILTER_STAGES", s.stages);
     }
+    if (s.pipe && (s.stages < 2 || s.stages > kMaxStages)) continue;
     if (s.pipe && !allow_pipe) continue;
     if (s.tile % (s.threads * s.ru) != 0 || s.prefetch < 1 || s.prefetch > kMaxPrefetch) continue;
     const int64_t tile = s.tile;
-    const int extra = s.pipe ? 2 : 1;  // ring chunks beyond what one step reads
+    const int extra = s.pipe ? s.stages : 1;  // ring chunks beyond what one step reads
     const int64_t h_back = ceil_div(int64_t(f.w_hi) + a.d, tile);
     const int64_t h_fwd = ceil_div(-int64_t(f.w_lo), tile);
     const int64_t nq_x = h_back + h_fwd + extra + s.prefetch;
@@ -1158,7 +1163,8 @@ int launch_strip(const FilterPlanHeader* hdr, const int32_t* h_terms, const int3
   if (pick.tile == 0) return PARRM_OK;  // rings do not fit: the caller falls back to the gather
 
   const int64_t tile = pick.tile;
-  const int extra = pick.pipe ? 2 : 1;
+  const int extra = pick.pipe ? pick.stages : 1;
+  a.stages = pick.stages;
   a.tile = pick.tile;
   a.prefetch = pick.prefetch;
   a.h_back = int32_t(ceil_div(int64_t(f.w_hi) + a.d, tile));
@@ -1230,7 +1236,9 @@ int launch_strip(const FilterPlanHeader* hdr, const int32_t* h_terms, const int3
     PARRM_PIPE_SHAPE(256, 128, 2) PARRM_PIPE_SHAPE(256, 128, 4) PARRM_PIPE_SHAPE(512, 128, 2)
     PARRM_PIPE_SHAPE(768, 256, 2) PARRM_PIPE_SHAPE(384, 256, 4) PARRM_PIPE_SHAPE(768, 128, 2)
     PARRM_PIPE_SHAPE(256, 256, 6) PARRM_PIPE_SHAPE(384, 128, 4) PARRM_PIPE_SHAPE(384, 384, 4)
-    PARRM_PIPE_SHAPE(256, 256, 8) PARRM_PIPE_SHAPE(512, 512, 4)
+    PARRM_PIPE_SHAPE(256, 256, 8) PARRM_PIPE_SHAPE(512, 512, 4) PARRM_PIPE_SHAPE(640, 256, 2)
+    PARRM_PIPE_SHAPE(320, 320, 4) PARRM_PIPE_SHAPE(512, 512, 2) PARRM_PIPE_SHAPE(256, 256, 5)
+    PARRM_PIPE_SHAPE(320, 256, 4) PARRM_PIPE_SHAPE(512, 512, 3)
 #undef PARRM_PIPE_SHAPE
   } else {
 #define PARRM_STRIP_SHAPE(NT_, RU_) \

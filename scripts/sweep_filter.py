@@ -58,11 +58,14 @@ def run(label, strategy, env):
 
 run("gather", _native.PLAN_GATHER, {})
 run("auto-default", _native.PLAN_AUTO, {})
-for pipe, threads, slide, ru, tile, pre, ctas in [
-    (1, 256, 256, 6, 1536, 2, 1), (1, 256, 256, 6, 1536, 1, 1), (1, 384, 256, 4, 1536, 2, 1),
-    (1, 256, 256, 8, 2048, 1, 1), (1, 512, 256, 4, 2048, 1, 1), (1, 512, 512, 4, 2048, 1, 1),
+for pipe, threads, slide, ru, tile, pre, ctas, stages in [
+    (1, 512, 512, 4, 2048, 1, 1, 2),
+    (1, 256, 256, 6, 1536, 1, 1, 3), (1, 512, 512, 3, 1536, 1, 1, 3),
+    (1, 320, 320, 4, 1280, 1, 1, 3), (1, 640, 256, 2, 1280, 1, 1, 3), (1, 256, 256, 5, 1280, 1, 1, 3),
+    (1, 512, 512, 2, 1024, 1, 1, 3), (1, 256, 256, 4, 1024, 2, 1, 3), (1, 512, 512, 2, 1024, 1, 1, 4),
 ]:
-    run(f"pipe{pipe} t{threads}+{slide} ru{ru} tile{tile} pre{pre} ctas{ctas}", _native.PLAN_AUTO,
+    run(f"pipe{pipe} t{threads}+{slide} ru{ru} tile{tile} pre{pre} ctas{ctas} stages{stages}",
+        _native.PLAN_AUTO,
         {"PARRM_FILTER_TILE": tile, "PARRM_FILTER_THREADS": threads, "PARRM_FILTER_RU": ru,
          "PARRM_FILTER_PREFETCH": pre, "PARRM_FILTER_CTAS": ctas, "PARRM_FILTER_PIPE": pipe,
-         "PARRM_FILTER_SLIDE": slide})
+         "PARRM_FILTER_SLIDE": slide, "PARRM_FILTER_STAGES": stages})

@@ -16,7 +16,8 @@ def _ceil_div(a, b):
 
 
 class StripModel:
-    def __init__(self, taps, desc, tile, prefetch=2, reinit_every=0, threads=256, pipe=False):
+    def __init__(self, taps, desc, tile, prefetch=2, reinit_every=0, threads=256, pipe=False,
+                 stages=2):
         self.taps = np.asarray(taps, dtype=np.int64)
         self.n_taps = len(self.taps)
         self.w_lo = min(int(self.taps[0]), 0)
@@ -24,7 +25,8 @@ class StripModel:
         self.tile = tile
         self.P = prefetch
         self.pipe = pipe
-        self.extra = 2 if pipe else 1  # ring chunks beyond what one step reads
+        self.stages = stages           # pipelined kernel: the slide runs stages - 1 chunks ahead
+        self.extra = stages if pipe else 1  # ring chunks beyond what one step reads
         self.reinit_every = reinit_every
         self.d = desc["stride"]
         self.nk = len(desc["windows"])
@@ -148,17 +150,19 @@ class StripModel:
                 self._gather(n, gamma + js * tile, t0, n_out, out)
                 land(js + self.h_fwd + 1)
         else:
-            # the slide warps run as far ahead as the hand-off barriers allow: slide(n + 1)
+            # the slide warps run as far ahead as the hand-off barriers allow: slide(n + stages - 1)
             # (and its TMA issue) completes before gather(n) starts
             def slide_step(n):
                 issue(js0 + n + self.h_fwd + self.P)
                 self._slide(n)
                 land(js0 + n + 1 + self.h_fwd)
 
-            slide_step(0)
+            ahead = self.stages - 1
+            for m in range(min(ahead, n_steps)):
+                slide_step(m)
             for n in range(n_steps):
-                if n + 1 < n_steps:
-                    slide_step(n + 1)
+                if n + ahead < n_steps:
+                    slide_step(n + ahead)
                 self._gather(n, gamma + (js0 + n) * tile, t0, n_out, out)
 
     def _slide(self, n):

@@ -108,12 +108,13 @@ MODEL_CASES = [
 ]
 
 
-@pytest.mark.parametrize("pipe", [False, True])
+@pytest.mark.parametrize("pipe", [0, 2, 3])
 @pytest.mark.parametrize("spec", MODEL_CASES)
 def test_strip_design_matches_oracle(spec, pipe):
     """Ring slots, mirror chunk, sliding boxes, piece boundaries and edge counts of the strip
     kernels (NumPy model with their index arithmetic) against the oracle's direct sum.
-    ``pipe`` models the producer/consumer kernel with the slide running a full chunk ahead."""
+    ``pipe`` = number of hand-over stages of the producer/consumer kernel (0: two-phase kernel);
+    the model runs the slide the full ``stages - 1`` chunks ahead of the gather."""
     case, n_total, tile, prefetch, gamma, pieces, reinit, chunk = spec
     period, phw, hw, omit, direction = CASES[case]
     taps = oracle.tap_offsets(period, period / 50 if phw is None else phw, hw, omit, direction)
@@ -121,7 +122,8 @@ def test_strip_design_matches_oracle(spec, pipe):
     rng = np.random.default_rng(case)
     x = rng.standard_normal((1, n_total)) + 3.0
     want = oracle.apply_filter_direct(x, taps)[0]
-    model = StripModel(taps, desc, tile, prefetch, 0 if pipe else reinit, pipe=pipe)
+    model = StripModel(taps, desc, tile, prefetch, 0 if pipe else reinit, pipe=bool(pipe),
+                       stages=max(pipe, 2))
     if chunk is None:
         got = model.run(x[0], 0, 0, n_total, n_total, gamma, pieces)
     else:
