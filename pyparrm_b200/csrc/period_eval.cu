@@ -569,6 +569,169 @@ eval_accumulate_ws_kernel(const double* __restrict__ y, const int64_t* __restric
 }
 
 // ------------------------------------------------------------------------------------------
+// Narrow form of the accumulate kernel for one or two channels (the bundled single-channel
+// example, cfg1, and the single-channel candidate sweeps, cfg5).  With so few right-hand sides
+// the W'Y products are 2 C FMAs per harmonic -- not worth a tensor-core tile that is 64 channels
+// wide -- so every thread is a generator: it walks the samples of its lane, carries its
+// harmonics' sums AND their products with y in registers, and the CTA reduces once at the end.
+// Same arithmetic and workspace layout as above (the K-half 1 partial is written as zeros).
+constexpr int kNarrowThreads = 256;
+constexpr int kNarrowBatch = 256;  // samples per sincos batch (one per thread)
+constexpr int kNarrowRowsPerGroup = (PARRM_MAX_BANDWIDTH + kGenGroups - 1) / kGenGroups;  // 6
+
+template <int C>
+__global__ void __launch_bounds__(kNarrowThreads, 2)
+eval_accumulate_narrow_kernel(const double* __restrict__ y, const int64_t* __restrict__ indices,
+                              const double* __restrict__ periods, double* __restrict__ ws,
+                              const EvalShape sh) {
+  __shared__ double2 s_cs[kNarrowBatch];
+  __shared__ double s_yv[kNarrowBatch * C];
+  const int tid = threadIdx.x;
+  const int64_t cand = blockIdx.x;
+  const int split = blockIdx.y;
+  const int bw = sh.bandwidth, two_bw = 2 * bw;
+  const int64_t n_begin = int64_t(split) * sh.split_len;
+  const int64_t n_end = min(n_begin + sh.split_len, sh.n_indices);
+  const double delta = 6.283185307179586 / periods[cand];  // 2*pi/period (parrm.py:619)
+  const int gi = tid & (kKT - 1), gg = tid / kKT;           // sample lane, harmonic residue group
+  const int h = (two_bw - gg + kGenGroups - 1) / kGenGroups;  // harmonics gg+1, gg+5, ... <= 2 bw
+  const int hb = (bw - gg + kGenGroups - 1) / kGenGroups;     // ... of which <= bw (rows of W)
+  double sum_c[kGenH], sum_s[kGenH];
+  double dot_c[kNarrowRowsPerGroup][C], dot_s[kNarrowRowsPerGroup][C], dot_1[C];
+#pragma unroll
+  for (int j = 0; j < kGenH; ++j) sum_c[j] = sum_s[j] = 0.0;
+#pragma unroll
+  for (int j = 0; j < kNarrowRowsPerGroup; ++j)
+#pragma unroll
+    for (int c = 0; c < C; ++c) dot_c[j][c] = dot_s[j][c] = 0.0;
+#pragma unroll
+  for (int c = 0; c < C; ++c) dot_1[c] = 0.0;
+
+  for (int64_t n_batch = n_begin; n_batch < n_end; n_batch += kNarrowBatch) {
+    __syncthreads();  // the previous batch has been consumed
+    {
+      const int64_t n = n_batch + tid;
+      double2 cs = make_double2(0.0, 0.0);
+      double yv[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) yv[c] = 0.0;
+      if (n < n_end) {
+        const double angle = double(indices[n] + 1) * delta;
+        sincos_phase(angle, &cs.y, &cs.x);
+#pragma unroll
+        for (int c = 0; c < C; ++c) yv[c] = y[n * sh.ld_y + c];
+      }
+      s_cs[tid] = cs;  // invalid samples: z = 0, y = 0 -> they add nothing below
+#pragma unroll
+      for (int c = 0; c < C; ++c) s_yv[tid * C + c] = yv[c];
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int sub = 0; sub < kNarrowBatch / kKT; ++sub) {
+      if (n_batch + sub * kKT >= n_end) break;  // uniform
+      const double2 z = s_cs[sub * kKT + gi];
+      double yv[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) yv[c] = s_yv[(sub * kKT + gi) * C + c];
+      if (gg == 0) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) dot_1[c] += yv[c];  // row 0 of W is the constant 1
+      }
+      double z2c = z.x, z2s = z.y;
+      cmul(z2c, z2s, z.x, z.y);
+      double z4c = z2c, z4s = z2s;
+      cmul(z4c, z4s, z2c, z2s);
+      double c = z.x, sn = z.y;  // seed z^(gg+1)
+      if (gg == 1) {
+        c = z2c; sn = z2s;
+      } else if (gg == 2) {
+        c = z2c; sn = z2s;
+        cmul(c, sn, z.x, z.y);
+      } else if (gg == 3) {
+        c = z4c; sn = z4s;
+      }
+#pragma unroll
+      for (int j = 0; j < kGenH; ++j) {
+        if (j >= h) break;  // uniform within a warp
+        if (j > 0) cmul(c, sn, z4c, z4s);
+        sum_c[j] += c;
+        sum_s[j] += sn;
+        if (j < kNarrowRowsPerGroup && j < hb) {
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) {
+            dot_c[j][ch] = fma(c, yv[ch], dot_c[j][ch]);
+            dot_s[j][ch] = fma(sn, yv[ch], dot_s[j][ch]);
+          }
+        }
+      }
+    }
+  }
+
+  // ---- reduce over the 64 sample lanes of every group (2 warps) and write ----
+  __shared__ double s_red[kNarrowThreads / 32][2 * kGenH + (2 * kNarrowRowsPerGroup + 1) * C];
+  const int warp = tid >> 5, lane = tid & 31;
+  {
+    int v = 0;
+#pragma unroll
+    for (int j = 0; j < kGenH; ++j) {
+      const double a = warp_sum(sum_c[j]), b = warp_sum(sum_s[j]);
+      if (lane == 0) {
+        s_red[warp][v] = a;
+        s_red[warp][v + 1] = b;
+      }
+      v += 2;
+    }
+#pragma unroll
+    for (int j = 0; j < kNarrowRowsPerGroup; ++j)
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) {
+        const double a = warp_sum(dot_c[j][ch]), b = warp_sum(dot_s[j][ch]);
+        if (lane == 0) {
+          s_red[warp][v] = a;
+          s_red[warp][v + 1] = b;
+        }
+        v += 2;
+      }
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) {
+      const double a = warp_sum(dot_1[ch]);
+      if (lane == 0) s_red[warp][v] = a;
+      ++v;
+    }
+  }
+  __syncthreads();
+  double* tp = ws + sh.t_offset + cand * sh.t_stride_period + int64_t(split) * sh.t_stride_split;
+  double* bp0 = ws + cand * sh.b_stride_period + (int64_t(split) * 2) * sh.b_stride_split;
+  double* bp1 = bp0 + sh.b_stride_split;
+  // harmonic sums
+  for (int e = tid; e < kGenGroups * kGenH; e += kNarrowThreads) {
+    const int g = e / kGenH, j = e % kGenH;
+    const int m = g + 1 + kGenGroups * j;
+    if (m <= two_bw) {
+      tp[m - 1] = s_red[2 * g][2 * j] + s_red[2 * g + 1][2 * j];
+      tp[two_bw + m - 1] = s_red[2 * g][2 * j + 1] + s_red[2 * g + 1][2 * j + 1];
+    }
+  }
+  // right-hand sides: rows 2m-1 (sin), 2m (cos), m = g + 1 + 4 j <= bw; row 0 from group 0
+  for (int e = tid; e < kGenGroups * kNarrowRowsPerGroup * C; e += kNarrowThreads) {
+    const int ch = e % C, j = (e / C) % kNarrowRowsPerGroup, g = e / (C * kNarrowRowsPerGroup);
+    const int m = g + 1 + kGenGroups * j;
+    if (m <= bw) {
+      const int v = 2 * kGenH + (j * C + ch) * 2;
+      bp0[int64_t(2 * m) * sh.n_chans + ch] = s_red[2 * g][v] + s_red[2 * g + 1][v];
+      bp0[int64_t(2 * m - 1) * sh.n_chans + ch] = s_red[2 * g][v + 1] + s_red[2 * g + 1][v + 1];
+      bp1[int64_t(2 * m) * sh.n_chans + ch] = 0.0;
+      bp1[int64_t(2 * m - 1) * sh.n_chans + ch] = 0.0;
+    }
+  }
+  if (tid < C) {
+    const int v = 2 * kGenH + 2 * kNarrowRowsPerGroup * C + tid;
+    bp0[tid] = s_red[0][v] + s_red[1][v];
+    bp1[tid] = 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 constexpr int kSolveThreads = 64;   // one channel per thread in the substitution phase; small, so
                                     // that three CTAs (M = 41) share an SM and hide each other's
                                     // dependent shared-memory chains
@@ -854,7 +1017,16 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
   double* ws = static_cast<double*>(d_workspace);
   dim3 grid((unsigned)n_periods, (unsigned)sh.n_splits, (unsigned)sh.n_chan_tiles);
   const char* two_phase = getenv("PARRM_EVAL_TWO_PHASE");
-  if (two_phase && *two_phase == '1') {
+  const char* no_narrow = getenv("PARRM_EVAL_NO_NARROW");
+  if (n_chans <= 2 && !(no_narrow && *no_narrow == '1')) {
+    dim3 narrow_grid((unsigned)n_periods, (unsigned)sh.n_splits, 1);
+    if (n_chans == 1)
+      eval_accumulate_narrow_kernel<1><<<narrow_grid, kNarrowThreads, 0, s>>>(d_y, d_indices,
+                                                                              d_periods, ws, sh);
+    else
+      eval_accumulate_narrow_kernel<2><<<narrow_grid, kNarrowThreads, 0, s>>>(d_y, d_indices,
+                                                                              d_periods, ws, sh);
+  } else if (two_phase && *two_phase == '1') {
     const size_t smem = size_t(kSuper * 16 + (kKT * kRowStride + 2 * kKT * kChanTile + 8 * 2 * kHMax) *
                                                  sizeof(double));
     PARRM_CUDA_OK(cudaFuncSetAttribute(eval_accumulate_kernel,
