@@ -313,6 +313,7 @@ constexpr int kWsThreads = kFmaThreads + kGenThreads;
 constexpr int kGenGroups = kGenThreads / kKT;
 constexpr int kGenH = (2 * PARRM_MAX_BANDWIDTH + kGenGroups - 1) / kGenGroups;  // harmonics per group
 constexpr int kTeamThreads = kGenThreads / 2;  // two generator teams produce alternate tiles
+constexpr int kGenH8 = (2 * PARRM_MAX_BANDWIDTH + 7) / 8;  // harmonics per residue class mod 8
 constexpr int kWsStages = 3;
 // Shared-memory tiles of the tensor-core path.  W is stored transposed, [row][sample], Y as
 // [sample][channel]; both with a row stride = 4 (mod 16) doubles, which makes the m8n8k4 fragment
@@ -365,16 +366,18 @@ eval_accumulate_ws_kernel(const double* __restrict__ y, const int64_t* __restric
     // (gi, gi + 32) of one harmonic group as independent chains.
     const int gt = tid - kFmaThreads;
     const int team = gt / kTeamThreads, tt = gt % kTeamThreads;
-    // harmonic group gg takes m = gg + 1, gg + 5, gg + 9, ...: seeds z^(gg+1) cost <= 3 complex
-    // products and every further harmonic one product by z^4 (short dependent chains)
+    // Harmonics are split into 8 residue classes: class r takes m = r + 1, r + 9, r + 17, ...,
+    // seeded with z^(r+1) and advanced by z^8.  A thread carries classes gg and gg + 4 of two
+    // samples: four independent chains of <= 9 dependent complex products (the generator is
+    // latency-bound: its FP64 instructions queue behind the tensor-core work on the same pipe).
     const int gi = tt & 31, gg = tt >> 5;
-    const int h = (two_bw - gg + kGenGroups - 1) / kGenGroups;  // harmonics of this group
+    const int h0 = (two_bw - gg + 7) / 8, h1 = (two_bw - gg + 3) / 8;  // harmonics per class
     const double delta = 6.283185307179586 / periods[cand];  // 2*pi/period (parrm.py:619)
     const bool pair_copies = (sh.ld_y % 2 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
     double2* cs_team = s_cs + team * kTeamThreads;
-    double sum_c[kGenH], sum_s[kGenH];
+    double sum0_c[kGenH8], sum0_s[kGenH8], sum1_c[kGenH8], sum1_s[kGenH8];
 #pragma unroll
-    for (int j = 0; j < kGenH; ++j) sum_c[j] = sum_s[j] = 0.0;
+    for (int j = 0; j < kGenH8; ++j) sum0_c[j] = sum0_s[j] = sum1_c[j] = sum1_s[j] = 0.0;
     int i = 0;  // index of the tile among this team's tiles
     for (int t = team; t < n_tiles; t += 2, ++i) {
       const int s = t % kWsStages;
@@ -415,25 +418,32 @@ eval_accumulate_ws_kernel(const double* __restrict__ y, const int64_t* __restric
         named_bar_sync(1 + team, kTeamThreads);
       }
       {
+        // samples past the end carry z = 0 (see the sincos batch), so every power, sum and W
+        // entry they produce is zero; only the constant row needs the explicit test
         const bool live_a = n_tile + gi < n_end, live_b = n_tile + gi + 32 < n_end;
         const double2 za = cs_team[(i & 1) * kKT + gi], zb = cs_team[(i & 1) * kKT + gi + 32];
-        // z^2, z^4 and the seed z^(gg+1) of both samples
-        double a2c = za.x, a2s = za.y, b2c = zb.x, b2s = zb.y;
+        double a2c = za.x, a2s = za.y, b2c = zb.x, b2s = zb.y;  // z^2
         cmul(a2c, a2s, za.x, za.y);
         cmul(b2c, b2s, zb.x, zb.y);
-        double a4c = a2c, a4s = a2s, b4c = b2c, b4s = b2s;
+        double a4c = a2c, a4s = a2s, b4c = b2c, b4s = b2s;      // z^4
         cmul(a4c, a4s, a2c, a2s);
         cmul(b4c, b4s, b2c, b2s);
-        double ca = za.x, sa = za.y, cb = zb.x, sb = zb.y;  // gg == 0: z
+        double a8c = a4c, a8s = a4s, b8c = b4c, b8s = b4s;      // z^8
+        cmul(a8c, a8s, a4c, a4s);
+        cmul(b8c, b8s, b4c, b4s);
+        double ca0 = za.x, sa0 = za.y, cb0 = zb.x, sb0 = zb.y;  // seed z^(gg+1); gg == 0: z
         if (gg == 1) {
-          ca = a2c; sa = a2s; cb = b2c; sb = b2s;
+          ca0 = a2c; sa0 = a2s; cb0 = b2c; sb0 = b2s;
         } else if (gg == 2) {
-          ca = a2c; sa = a2s; cb = b2c; sb = b2s;
-          cmul(ca, sa, za.x, za.y);
-          cmul(cb, sb, zb.x, zb.y);
+          ca0 = a2c; sa0 = a2s; cb0 = b2c; sb0 = b2s;
+          cmul(ca0, sa0, za.x, za.y);
+          cmul(cb0, sb0, zb.x, zb.y);
         } else if (gg == 3) {
-          ca = a4c; sa = a4s; cb = b4c; sb = b4s;
+          ca0 = a4c; sa0 = a4s; cb0 = b4c; sb0 = b4s;
         }
+        double ca1 = ca0, sa1 = sa0, cb1 = cb0, sb1 = sb0;      // seed z^(gg+5)
+        cmul(ca1, sa1, a4c, a4s);
+        cmul(cb1, sb1, b4c, b4s);
         double* wcol = s_w + s * kWtTile + gi;  // wcol[row * kWtStride (+ 32)] = W[sample][row]
         if (gg == 0) {
           wcol[0] = live_a ? 1.0 : 0.0;
@@ -442,26 +452,32 @@ eval_accumulate_ws_kernel(const double* __restrict__ y, const int64_t* __restric
         if (gg == kGenGroups - 1)
           for (int r = n_rows; r < kRowsPad; ++r) wcol[r * kWtStride] = wcol[r * kWtStride + 32] = 0.0;
 #pragma unroll
-        for (int j = 0; j < kGenH; ++j) {
-          if (j >= h) break;  // uniform within a warp (one group per warp)
+        for (int j = 0; j < kGenH8; ++j) {
+          if (j >= h0) break;  // uniform within a warp (h1 <= h0)
           if (j > 0) {
-            cmul(ca, sa, a4c, a4s);
-            cmul(cb, sb, b4c, b4s);
+            cmul(ca0, sa0, a8c, a8s);
+            cmul(cb0, sb0, b8c, b8s);
+            cmul(ca1, sa1, a8c, a8s);
+            cmul(cb1, sb1, b8c, b8s);
           }
-          const int m = gg + 1 + kGenGroups * j;  // <= two_bw by the choice of h
-          if (live_a) {
-            sum_c[j] += ca;
-            sum_s[j] += sa;
+          const int m_lo = gg + 1 + 8 * j, m_hi = m_lo + 4;
+          sum0_c[j] += ca0 + cb0;
+          sum0_s[j] += sa0 + sb0;
+          if (m_lo <= bw) {  // columns 2m-1 = sin, 2m = cos (parrm.py:622-623)
+            wcol[(2 * m_lo - 1) * kWtStride] = sa0;
+            wcol[(2 * m_lo) * kWtStride] = ca0;
+            wcol[(2 * m_lo - 1) * kWtStride + 32] = sb0;
+            wcol[(2 * m_lo) * kWtStride + 32] = cb0;
           }
-          if (live_b) {
-            sum_c[j] += cb;
-            sum_s[j] += sb;
-          }
-          if (m <= bw) {  // columns 2m-1 = sin, 2m = cos (parrm.py:622-623)
-            wcol[(2 * m - 1) * kWtStride] = live_a ? sa : 0.0;
-            wcol[(2 * m) * kWtStride] = live_a ? ca : 0.0;
-            wcol[(2 * m - 1) * kWtStride + 32] = live_b ? sb : 0.0;
-            wcol[(2 * m) * kWtStride + 32] = live_b ? cb : 0.0;
+          if (j < h1) {
+            sum1_c[j] += ca1 + cb1;
+            sum1_s[j] += sa1 + sb1;
+            if (m_hi <= bw) {
+              wcol[(2 * m_hi - 1) * kWtStride] = sa1;
+              wcol[(2 * m_hi) * kWtStride] = ca1;
+              wcol[(2 * m_hi - 1) * kWtStride + 32] = sb1;
+              wcol[(2 * m_hi) * kWtStride + 32] = cb1;
+            }
           }
         }
       }
@@ -471,24 +487,30 @@ eval_accumulate_ws_kernel(const double* __restrict__ y, const int64_t* __restric
     }
     // harmonic sums: reduce over the sample lanes and the two teams (channel tile 0 only)
     if (ctile == 0) {
-      const int warp = gt >> 5, lane = gt & 31;  // warp = team * 4 + group
+      const int warp = gt >> 5, lane = gt & 31;  // warp = team * 4 + gg
+      double* mine = s_red + warp * 4 * kGenH8;  // [class gg: c, s][class gg + 4: c, s]
 #pragma unroll
-      for (int j = 0; j < kGenH; ++j) {
-        const double c = warp_sum(sum_c[j]);
-        const double sn = warp_sum(sum_s[j]);
+      for (int j = 0; j < kGenH8; ++j) {
+        const double c0 = warp_sum(sum0_c[j]), s0 = warp_sum(sum0_s[j]);
+        const double c1 = warp_sum(sum1_c[j]), s1 = warp_sum(sum1_s[j]);
         if (lane == 0) {
-          s_red[warp * 2 * kGenH + j] = c;
-          s_red[warp * 2 * kGenH + kGenH + j] = sn;
+          mine[j] = c0;
+          mine[kGenH8 + j] = s0;
+          mine[2 * kGenH8 + j] = c1;
+          mine[3 * kGenH8 + j] = s1;
         }
       }
       named_bar_sync(3, kGenThreads);
       double* tp = ws + sh.t_offset + cand * sh.t_stride_period + int64_t(split) * sh.t_stride_split;
-      for (int e = gt; e < kGenGroups * kGenH; e += kGenThreads) {
-        const int g = e / kGenH, j = e % kGenH;
-        const int m = g + 1 + kGenGroups * j;  // harmonic j of group g
+      for (int e = gt; e < 8 * kGenH8; e += kGenThreads) {
+        const int r = e / kGenH8, j = e % kGenH8;  // residue class, harmonic m = r + 1 + 8 j
+        const int m = r + 1 + 8 * j;
         if (m <= two_bw) {
-          tp[m - 1] = s_red[g * 2 * kGenH + j] + s_red[(g + 4) * 2 * kGenH + j];
-          tp[two_bw + m - 1] = s_red[g * 2 * kGenH + kGenH + j] + s_red[(g + 4) * 2 * kGenH + kGenH + j];
+          const int g = r & 3, hi = r >> 2;
+          const double* wa = s_red + g * 4 * kGenH8 + hi * 2 * kGenH8;        // team 0
+          const double* wb = s_red + (g + 4) * 4 * kGenH8 + hi * 2 * kGenH8;  // team 1
+          tp[m - 1] = wa[j] + wb[j];
+          tp[two_bw + m - 1] = wa[kGenH8 + j] + wb[kGenH8 + j];
         }
       }
     }
