@@ -54,6 +54,8 @@ struct EvalShape {
   int64_t t_stride_split;         // 4 * bw   (C_1..C_2bw, S_1..S_2bw)
   int64_t t_stride_period;        // n_splits * t_stride_split
   int64_t t_offset;               // start of the harmonic-sum area
+  int64_t c_offset;               // start of the per-channel sums of y (row 0 of W'Y)
+  int row0_from_colsum;           // 1: the accumulate kernel leaves row 0 to eval_colsum_kernel
 };
 
 __device__ __forceinline__ void cmul(double& c, double& s, double c2, double s2) {
@@ -419,8 +421,7 @@ eval_accumulate_ws_kernel(const double* __restrict__ y, const int64_t* __restric
       }
       {
         // samples past the end carry z = 0 (see the sincos batch), so every power, sum and W
-        // entry they produce is zero; only the constant row needs the explicit test
-        const bool live_a = n_tile + gi < n_end, live_b = n_tile + gi + 32 < n_end;
+        // entry they produce is zero
         const double2 za = cs_team[(i & 1) * kKT + gi], zb = cs_team[(i & 1) * kKT + gi + 32];
         double a2c = za.x, a2s = za.y, b2c = zb.x, b2s = zb.y;  // z^2
         cmul(a2c, a2s, za.x, za.y);
@@ -445,12 +446,9 @@ eval_accumulate_ws_kernel(const double* __restrict__ y, const int64_t* __restric
         cmul(ca1, sa1, a4c, a4s);
         cmul(cb1, sb1, b4c, b4s);
         double* wcol = s_w + s * kWtTile + gi;  // wcol[row * kWtStride (+ 32)] = W[sample][row]
-        if (gg == 0) {
-          wcol[0] = live_a ? 1.0 : 0.0;
-          wcol[32] = live_b ? 1.0 : 0.0;
-        }
+        // tile row r holds column r + 1 of W (the constant column is handled by eval_colsum_kernel)
         if (gg == kGenGroups - 1)
-          for (int r = n_rows; r < kRowsPad; ++r) wcol[r * kWtStride] = wcol[r * kWtStride + 32] = 0.0;
+          for (int r = n_rows - 1; r < kRowsPad; ++r) wcol[r * kWtStride] = wcol[r * kWtStride + 32] = 0.0;
 #pragma unroll
         for (int j = 0; j < kGenH8; ++j) {
           if (j >= h0) break;  // uniform within a warp (h1 <= h0)
@@ -464,19 +462,19 @@ eval_accumulate_ws_kernel(const double* __restrict__ y, const int64_t* __restric
           sum0_c[j] += ca0 + cb0;
           sum0_s[j] += sa0 + sb0;
           if (m_lo <= bw) {  // columns 2m-1 = sin, 2m = cos (parrm.py:622-623)
-            wcol[(2 * m_lo - 1) * kWtStride] = sa0;
-            wcol[(2 * m_lo) * kWtStride] = ca0;
-            wcol[(2 * m_lo - 1) * kWtStride + 32] = sb0;
-            wcol[(2 * m_lo) * kWtStride + 32] = cb0;
+            wcol[(2 * m_lo - 2) * kWtStride] = sa0;
+            wcol[(2 * m_lo - 1) * kWtStride] = ca0;
+            wcol[(2 * m_lo - 2) * kWtStride + 32] = sb0;
+            wcol[(2 * m_lo - 1) * kWtStride + 32] = cb0;
           }
           if (j < h1) {
             sum1_c[j] += ca1 + cb1;
             sum1_s[j] += sa1 + sb1;
             if (m_hi <= bw) {
-              wcol[(2 * m_hi - 1) * kWtStride] = sa1;
-              wcol[(2 * m_hi) * kWtStride] = ca1;
-              wcol[(2 * m_hi - 1) * kWtStride + 32] = sb1;
-              wcol[(2 * m_hi) * kWtStride + 32] = cb1;
+              wcol[(2 * m_hi - 2) * kWtStride] = sa1;
+              wcol[(2 * m_hi - 1) * kWtStride] = ca1;
+              wcol[(2 * m_hi - 2) * kWtStride + 32] = sb1;
+              wcol[(2 * m_hi - 1) * kWtStride + 32] = cb1;
             }
           }
         }
@@ -525,7 +523,7 @@ eval_accumulate_ws_kernel(const double* __restrict__ y, const int64_t* __restric
   // channels 16 nq..+16, all row blocks of 8.
   const int warp = tid >> 5, l = tid & 31;
   const int kh = warp >> 2, nq = warp & 3;
-  const int n_mb = (n_rows + 7) >> 3;  // row blocks in use (<= 6)
+  const int n_mb = (n_rows - 1 + 7) >> 3;  // row blocks in use (<= 6): tile row r = W column r + 1
   double acc[6][2][2];
 #pragma unroll
   for (int mb = 0; mb < 6; ++mb)
@@ -576,7 +574,7 @@ eval_accumulate_ws_kernel(const double* __restrict__ y, const int64_t* __restric
     double* bp = ws + cand * sh.b_stride_period + (int64_t(split) * 2 + kh) * sh.b_stride_split;
 #pragma unroll
     for (int mb = 0; mb < 6; ++mb) {
-      const int row = mb * 8 + (l >> 2);
+      const int row = mb * 8 + (l >> 2) + 1;
       if (row < n_rows) {
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb)
@@ -585,6 +583,433 @@ eval_accumulate_ws_kernel(const double* __restrict__ y, const int64_t* __restric
             const int ch = nq * 16 + nb * 8 + 2 * (l & 3) + j;
             if (ch < n_chan_here) bp[int64_t(row) * sh.n_chans + chan0 + ch] = acc[mb][nb][j];
           }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Two-phase tensor-core form: every warp first generates (harmonics of a 64-sample tile, all
+// 256 threads, throughput-bound) and then multiplies (DMMA); two CTAs per SM run out of phase,
+// so one CTA's generation hides behind the other's tensor work.  Shares the tile layouts of the
+// warp-specialised kernel and the residue-mod-4 harmonic groups.
+__global__ void __launch_bounds__(kAccThreads, 2)
+eval_accumulate_tc2_kernel(const double* __restrict__ y, const int64_t* __restrict__ indices,
+                           const double* __restrict__ periods, double* __restrict__ ws,
+                           const EvalShape sh) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* s_cs = reinterpret_cast<double2*>(smem_raw);                  // [kSuper] (cos, sin)
+  double* s_w = reinterpret_cast<double*>(smem_raw + kSuper * 16);       // [kRowsPad][kWtStride]
+  double* s_y = s_w + kWtTile;                                           // 2 x [kKT][kYStride]
+  double* s_red = s_y + 2 * kYTile;                                      // [8 warps][2 * kHMax]
+  constexpr int H = kHMax;
+
+  const int tid = threadIdx.x;
+  const int64_t cand = blockIdx.x;
+  const int split = blockIdx.y;
+  const int ctile = blockIdx.z;
+  const int bw = sh.bandwidth, two_bw = 2 * bw;
+  const int n_rows = sh.n_rows;
+  const int64_t n_begin = int64_t(split) * sh.split_len;
+  const int64_t n_end = min(n_begin + sh.split_len, sh.n_indices);
+  const int chan0 = ctile * kChanTile;
+  const int n_chan_here = int(min64(kChanTile, sh.n_chans - chan0));
+  const double delta = 6.283185307179586 / periods[cand];  // 2*pi/period (parrm.py:619)
+  const bool pair_copies = (sh.ld_y % 2 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+
+  // generator role: sample lane gi, residue group gg -> harmonics gg+1, gg+5, ...
+  const int gi = tid & (kKT - 1), gg = tid / kKT;
+  const int h = (two_bw - gg + kGroups - 1) / kGroups;
+  double sum_c[H], sum_s[H];
+#pragma unroll
+  for (int j = 0; j < H; ++j) sum_c[j] = sum_s[j] = 0.0;
+  // tensor role: warp (kh, nq): samples kh*32..+32 of the tile, channels 16 nq..+16
+  const int warp = tid >> 5, l = tid & 31;
+  const int kh = warp >> 2, nq = warp & 3;
+  const int n_mb = (n_rows - 1 + 7) >> 3;
+  double acc[6][2][2];
+#pragma unroll
+  for (int mb = 0; mb < 6; ++mb)
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+
+  auto stage_y = [&](int buf, int64_t n_tile) {
+    double* dst = s_y + buf * kYTile;
+    if (pair_copies) {
+      const int c = (tid & 31) * 2, k0 = tid >> 5;
+      const bool c_ok = c < n_chan_here;
+      for (int k = k0; k < kKT; k += kAccThreads / 32) {
+        const int64_t n = n_tile + k;
+        const bool ok = n < n_end && c_ok;
+        const int bytes = !ok ? 0 : (c + 1 < n_chan_here ? 16 : 8);
+        cp_async16(dst + k * kYStride + c, ok ? y + n * sh.ld_y + chan0 + c : y, bytes);
+      }
+    } else {
+      const int c = tid & 63, k0 = tid >> 6;
+      for (int k = k0; k < kKT; k += kAccThreads / 64) {
+        const int64_t n = n_tile + k;
+        const bool ok = n < n_end && c < n_chan_here;
+        cp_async8(dst + k * kYStride + c, ok ? y + n * sh.ld_y + chan0 + c : y, ok ? 8 : 0);
+      }
+    }
+    cp_async_commit();
+  };
+  int y_buf = 0;
+  if (n_begin < n_end) stage_y(0, n_begin);
+
+  for (int64_t n_super = n_begin; n_super < n_end; n_super += kSuper) {
+    {  // one accurate sincos per sample of this batch; samples past the end hold z = 0
+      const int64_t n = n_super + tid;
+      double2 cs = make_double2(0.0, 0.0);
+      if (n < n_end) {
+        const double angle = double(indices[n] + 1) * delta;
+        sincos_phase(angle, &cs.y, &cs.x);
+      }
+      s_cs[tid] = cs;
+    }
+    __syncthreads();
+    for (int sub = 0; sub < kSuper / kKT; ++sub) {
+      const int64_t n_tile = n_super + sub * kKT;
+      if (n_tile >= n_end) break;  // uniform
+      {  // ---- generate the harmonics of kKT samples (W stored transposed) ----
+        const double2 z = s_cs[sub * kKT + gi];
+        double z2c = z.x, z2s = z.y;
+        cmul(z2c, z2s, z.x, z.y);
+        double z4c = z2c, z4s = z2s;
+        cmul(z4c, z4s, z2c, z2s);
+        double c = z.x, sn = z.y;  // seed z^(gg+1)
+        if (gg == 1) {
+          c = z2c; sn = z2s;
+        } else if (gg == 2) {
+          c = z2c; sn = z2s;
+          cmul(c, sn, z.x, z.y);
+        } else if (gg == 3) {
+          c = z4c; sn = z4s;
+        }
+        double* wcol = s_w + gi;
+        // tile row r holds column r + 1 of W (the constant column: eval_colsum_kernel)
+        if (gg == kGroups - 1)
+          for (int r = n_rows - 1; r < kRowsPad; ++r) wcol[r * kWtStride] = 0.0;
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+          if (j >= h) break;  // uniform within a warp
+          if (j > 0) cmul(c, sn, z4c, z4s);
+          const int m = gg + 1 + kGroups * j;
+          sum_c[j] += c;
+          sum_s[j] += sn;
+          if (m <= bw) {  // columns 2m-1 = sin, 2m = cos (parrm.py:622-623)
+            wcol[(2 * m - 2) * kWtStride] = sn;
+            wcol[(2 * m - 1) * kWtStride] = c;
+          }
+        }
+      }
+      if (n_tile + kKT < n_end) {  // this tile's Y has been in flight; start the next one
+        stage_y(y_buf ^ 1, n_tile + kKT);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      {  // ---- B += W' Y on the FP64 tensor cores ----
+        const double* wa = s_w + (l >> 2) * kWtStride + kh * (kKT / 2) + (l & 3);
+        const double* yb = s_y + y_buf * kYTile + (kh * (kKT / 2) + (l & 3)) * kYStride + nq * 16 + (l >> 2);
+#pragma unroll 2
+        for (int step = 0; step < kKT / 8; ++step) {
+          double a[6], b[2];
+#pragma unroll
+          for (int mb = 0; mb < 6; ++mb) a[mb] = mb < n_mb ? wa[mb * 8 * kWtStride + step * 4] : 0.0;
+          b[0] = yb[step * 4 * kYStride];
+          b[1] = yb[step * 4 * kYStride + 8];
+#pragma unroll
+          for (int mb = 0; mb < 6; ++mb) {
+            if (mb < n_mb) {
+#pragma unroll
+              for (int nb = 0; nb < 2; ++nb)
+                asm volatile(
+                    "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                    : "+d"(acc[mb][nb][0]), "+d"(acc[mb][nb][1])
+                    : "d"(a[mb]), "d"(b[nb]));
+            }
+          }
+        }
+      }
+      __syncthreads();
+      y_buf ^= 1;
+    }
+  }
+
+  {  // ---- write the B partial of this (candidate, split, K-half) ----
+    double* bp = ws + cand * sh.b_stride_period + (int64_t(split) * 2 + kh) * sh.b_stride_split;
+#pragma unroll
+    for (int mb = 0; mb < 6; ++mb) {
+      const int row = mb * 8 + (l >> 2) + 1;
+      if (row < n_rows) {
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int ch = nq * 16 + nb * 8 + 2 * (l & 3) + j;
+            if (ch < n_chan_here) bp[int64_t(row) * sh.n_chans + chan0 + ch] = acc[mb][nb][j];
+          }
+      }
+    }
+  }
+  if (ctile == 0) {  // ---- harmonic sums: reduce the kKT sample lanes of each group ----
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+      const double c = warp_sum(sum_c[j]);
+      const double sn = warp_sum(sum_s[j]);
+      if (l == 0) {
+        s_red[warp * 2 * H + j] = c;
+        s_red[warp * 2 * H + H + j] = sn;
+      }
+    }
+    __syncthreads();
+    double* tp = ws + sh.t_offset + cand * sh.t_stride_period + int64_t(split) * sh.t_stride_split;
+    for (int e = tid; e < kGroups * H; e += kAccThreads) {
+      const int g = e / H, j = e % H;
+      const int m = g + 1 + kGroups * j;
+      if (m <= two_bw) {
+        tp[m - 1] = s_red[(2 * g) * 2 * H + j] + s_red[(2 * g + 1) * 2 * H + j];
+        tp[two_bw + m - 1] = s_red[(2 * g) * 2 * H + H + j] + s_red[(2 * g + 1) * 2 * H + H + j];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Alternating tensor-core form (default for more than two channels).  Measured on the two
+// overlapped forms above: a DMMA holds the FP64 pipe for 16 cycles, so scalar FP64 instructions
+// of other warps (the generator's dependent complex products) wait ~10x longer behind tensor
+// work than on an idle pipe -- overlapping generation with DMMA costs more than it hides.  Here
+// one 512-thread CTA per SM alternates: all 16 warps generate a 64-sample tile (one residue
+// class mod 8 of one sample per thread: <= 10 dependent complex products, tensor pipe idle),
+// then all 16 warps multiply it (DMMA only).  Y tiles still stream in through cp.async a tile
+// ahead.  Same tile layouts, arithmetic and workspace as the other tensor forms.
+constexpr int kSoloThreads = 512;
+constexpr int kSoloBatch = kSoloThreads;  // samples per sincos batch (one per thread)
+constexpr int kSoloKT = 128;              // samples per tile: two per thread while generating
+constexpr int kSoloWtStride = 132;        // >= kSoloKT, = 4 (mod 16)
+constexpr int kSoloWtTile = kRowsPad * kSoloWtStride;
+constexpr int kSoloYTile = kSoloKT * kYStride;
+
+template <int N>
+struct IntTag {
+  static constexpr int value = N;
+};
+
+template <int N_MB>  // 8-row blocks of W' in use: ceil(2 bw / 8)
+__global__ void __launch_bounds__(kSoloThreads, 1)
+eval_accumulate_solo_kernel(const double* __restrict__ y, const int64_t* __restrict__ indices,
+                            const double* __restrict__ periods, double* __restrict__ ws,
+                            const EvalShape sh) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* s_cs = reinterpret_cast<double2*>(smem_raw);                   // [kSoloBatch] (cos, sin)
+  double* s_w = reinterpret_cast<double*>(smem_raw + kSoloBatch * 16);    // [kRowsPad][kSoloWtStride]
+  double* s_y = s_w + kSoloWtTile;                                        // 2 x [kSoloKT][kYStride]
+  double* s_red = s_y + 2 * kSoloYTile;                                   // [16 warps][2 * kGenH8]
+
+  const int tid = threadIdx.x;
+  const int64_t cand = blockIdx.x;
+  const int split = blockIdx.y;
+  const int ctile = blockIdx.z;
+  const int bw = sh.bandwidth, two_bw = 2 * bw;
+  const int n_rows = sh.n_rows;
+  const int64_t n_begin = int64_t(split) * sh.split_len;
+  const int64_t n_end = min(n_begin + sh.split_len, sh.n_indices);
+  const int chan0 = ctile * kChanTile;
+  const int n_chan_here = int(min64(kChanTile, sh.n_chans - chan0));
+  const double delta = 6.283185307179586 / periods[cand];  // 2*pi/period (parrm.py:619)
+  const bool pair_copies = (sh.ld_y % 2 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+
+  // generator role: samples gi and gi + 64 of the tile (two independent chains per thread: the
+  // complex products are latency-bound), residue class r8 -> harmonics r8+1, r8+9, r8+17, ...
+  const int gi = tid & 63, r8 = tid >> 6;
+  const int h = (two_bw - r8 + 7) / 8;
+  double sum_c[kGenH8], sum_s[kGenH8];
+#pragma unroll
+  for (int j = 0; j < kGenH8; ++j) sum_c[j] = sum_s[j] = 0.0;
+  // tensor role: warp (kh, nq, mh): samples kh*64..+64, channels 16 nq..+16, row blocks
+  // 0..2 (mh = 0) or 3..5 (mh = 1)
+  const int warp = tid >> 5, l = tid & 31;
+  // (warp & 3 picks the scheduler partition: each partition gets both row halves and K halves)
+  const int kh = warp >> 3, mh = (warp >> 2) & 1, nq = warp & 3;
+  // tile row r = W column r + 1 (row 0: eval_colsum_kernel); a warp with mh = 0 takes the first
+  // kCnt0 row blocks, mh = 1 the remaining kCnt1 -- compile-time counts, so that the DMMA
+  // sequence below is straight-line code (mma.sync inside runtime conditionals costs a
+  // WARPSYNC and NOPs per instruction)
+  constexpr int kCnt0 = (N_MB + 1) / 2, kCnt1 = N_MB / 2;
+  double acc[3][2][2];
+#pragma unroll
+  for (int mb = 0; mb < 3; ++mb)
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+
+  auto stage_y = [&](int buf, int64_t n_tile) {
+    double* dst = s_y + buf * kSoloYTile;
+    if (pair_copies) {
+      const int c = (tid & 31) * 2, k0 = tid >> 5;
+      const bool c_ok = c < n_chan_here;
+      for (int k = k0; k < kSoloKT; k += kSoloThreads / 32) {
+        const int64_t n = n_tile + k;
+        const bool ok = n < n_end && c_ok;
+        const int bytes = !ok ? 0 : (c + 1 < n_chan_here ? 16 : 8);
+        cp_async16(dst + k * kYStride + c, ok ? y + n * sh.ld_y + chan0 + c : y, bytes);
+      }
+    } else {
+      const int c = tid & 63, k0 = tid >> 6;
+      for (int k = k0; k < kSoloKT; k += kSoloThreads / 64) {
+        const int64_t n = n_tile + k;
+        const bool ok = n < n_end && c < n_chan_here;
+        cp_async8(dst + k * kYStride + c, ok ? y + n * sh.ld_y + chan0 + c : y, ok ? 8 : 0);
+      }
+    }
+    cp_async_commit();
+  };
+  int y_buf = 0;
+  if (n_begin < n_end) stage_y(0, n_begin);
+
+  for (int64_t n_super = n_begin; n_super < n_end; n_super += kSoloBatch) {
+    {  // one accurate sincos per sample of this batch; samples past the end hold z = 0
+      const int64_t n = n_super + tid;
+      double2 cs = make_double2(0.0, 0.0);
+      if (n < n_end) {
+        const double angle = double(indices[n] + 1) * delta;
+        sincos_phase(angle, &cs.y, &cs.x);
+      }
+      s_cs[tid] = cs;
+    }
+    __syncthreads();
+    for (int sub = 0; sub < kSoloBatch / kSoloKT; ++sub) {
+      const int64_t n_tile = n_super + sub * kSoloKT;
+      if (n_tile >= n_end) break;  // uniform
+#ifndef PARRM_DEBUG_SOLO_NO_GEN
+      {  // ---- generate: class r8 of samples gi, gi + 64 (W transposed, tile row = column - 1) ----
+        const double2 za = s_cs[sub * kSoloKT + gi], zb = s_cs[sub * kSoloKT + gi + 64];
+        double a2c = za.x, a2s = za.y, b2c = zb.x, b2s = zb.y;
+        cmul(a2c, a2s, za.x, za.y);
+        cmul(b2c, b2s, zb.x, zb.y);
+        double a4c = a2c, a4s = a2s, b4c = b2c, b4s = b2s;
+        cmul(a4c, a4s, a2c, a2s);
+        cmul(b4c, b4s, b2c, b2s);
+        double a8c = a4c, a8s = a4s, b8c = b4c, b8s = b4s;
+        cmul(a8c, a8s, a4c, a4s);
+        cmul(b8c, b8s, b4c, b4s);
+        double ca = za.x, sa = za.y, cb = zb.x, sb = zb.y;  // seed z^(r8+1)
+        switch (r8) {
+          case 1: ca = a2c; sa = a2s; cb = b2c; sb = b2s; break;
+          case 2: ca = a2c; sa = a2s; cb = b2c; sb = b2s;
+                  cmul(ca, sa, za.x, za.y); cmul(cb, sb, zb.x, zb.y); break;
+          case 3: ca = a4c; sa = a4s; cb = b4c; sb = b4s; break;
+          case 4: ca = a4c; sa = a4s; cb = b4c; sb = b4s;
+                  cmul(ca, sa, za.x, za.y); cmul(cb, sb, zb.x, zb.y); break;
+          case 5: ca = a4c; sa = a4s; cb = b4c; sb = b4s;
+                  cmul(ca, sa, a2c, a2s); cmul(cb, sb, b2c, b2s); break;
+          case 6: ca = a8c; sa = a8s; cb = b8c; sb = b8s;  // z^8 * conj(z) = z^7 (|z| = 1)
+                  cmul(ca, sa, za.x, -za.y); cmul(cb, sb, zb.x, -zb.y); break;
+          case 7: ca = a8c; sa = a8s; cb = b8c; sb = b8s; break;
+          default: break;
+        }
+        double* wcol = s_w + gi;
+        if (r8 == 7)
+          for (int r = n_rows - 1; r < kRowsPad; ++r)
+            wcol[r * kSoloWtStride] = wcol[r * kSoloWtStride + 64] = 0.0;
+#pragma unroll
+        for (int j = 0; j < kGenH8; ++j) {
+          if (j >= h) break;  // uniform within a warp
+          if (j > 0) {
+            cmul(ca, sa, a8c, a8s);
+            cmul(cb, sb, b8c, b8s);
+          }
+          const int m = r8 + 1 + 8 * j;
+          sum_c[j] += ca + cb;
+          sum_s[j] += sa + sb;
+          if (m <= bw) {  // columns 2m-1 = sin, 2m = cos (parrm.py:622-623)
+            wcol[(2 * m - 2) * kSoloWtStride] = sa;
+            wcol[(2 * m - 1) * kSoloWtStride] = ca;
+            wcol[(2 * m - 2) * kSoloWtStride + 64] = sb;
+            wcol[(2 * m - 1) * kSoloWtStride + 64] = cb;
+          }
+        }
+      }
+#endif
+      if (n_tile + kSoloKT < n_end) {  // this tile's Y has been in flight; start the next one
+        stage_y(y_buf ^ 1, n_tile + kSoloKT);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+#ifndef PARRM_DEBUG_SOLO_NO_MMA
+      {  // ---- multiply: B += W' Y on the FP64 tensor cores, every warp ----
+        const double* yb =
+            s_y + y_buf * kSoloYTile + (kh * (kSoloKT / 2) + (l & 3)) * kYStride + nq * 16 + (l >> 2);
+        auto multiply = [&](auto count, int first_block) {
+          constexpr int CNT = decltype(count)::value;
+          const double* wa =
+              s_w + (first_block * 8 + (l >> 2)) * kSoloWtStride + kh * (kSoloKT / 2) + (l & 3);
+#pragma unroll 2
+          for (int step = 0; step < kSoloKT / 8; ++step) {
+            double a[CNT > 0 ? CNT : 1], b[2];
+#pragma unroll
+            for (int mb = 0; mb < CNT; ++mb) a[mb] = wa[mb * 8 * kSoloWtStride + step * 4];
+            b[0] = yb[step * 4 * kYStride];
+            b[1] = yb[step * 4 * kYStride + 8];
+#pragma unroll
+            for (int mb = 0; mb < CNT; ++mb)
+#pragma unroll
+              for (int nb = 0; nb < 2; ++nb)
+                asm volatile(
+                    "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                    : "+d"(acc[mb][nb][0]), "+d"(acc[mb][nb][1])
+                    : "d"(a[mb]), "d"(b[nb]));
+          }
+        };
+        if (mh == 0) multiply(IntTag<kCnt0>{}, 0);
+        else multiply(IntTag<kCnt1>{}, kCnt0);
+      }
+#endif
+      __syncthreads();
+      y_buf ^= 1;
+    }
+  }
+
+  {  // ---- write the B partial of this (candidate, split, K-half) ----
+    double* bp = ws + cand * sh.b_stride_period + (int64_t(split) * 2 + kh) * sh.b_stride_split;
+#pragma unroll
+    for (int mb = 0; mb < 3; ++mb) {
+      const int row = ((mh ? kCnt0 : 0) + mb) * 8 + (l >> 2) + 1;
+      if (mb < (mh ? kCnt1 : kCnt0) && row < n_rows) {
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int ch = nq * 16 + nb * 8 + 2 * (l & 3) + j;
+            if (ch < n_chan_here) bp[int64_t(row) * sh.n_chans + chan0 + ch] = acc[mb][nb][j];
+          }
+      }
+    }
+  }
+  if (ctile == 0) {  // ---- harmonic sums: reduce the kKT sample lanes (2 warps) of each class ----
+#pragma unroll
+    for (int j = 0; j < kGenH8; ++j) {
+      const double c = warp_sum(sum_c[j]);
+      const double sn = warp_sum(sum_s[j]);
+      if (l == 0) {
+        s_red[warp * 2 * kGenH8 + j] = c;
+        s_red[warp * 2 * kGenH8 + kGenH8 + j] = sn;
+      }
+    }
+    __syncthreads();
+    double* tp = ws + sh.t_offset + cand * sh.t_stride_period + int64_t(split) * sh.t_stride_split;
+    for (int e = tid; e < 8 * kGenH8; e += kSoloThreads) {
+      const int r = e / kGenH8, j = e % kGenH8;
+      const int m = r + 1 + 8 * j;
+      if (m <= two_bw) {
+        const double* wa = s_red + (2 * r) * 2 * kGenH8;
+        const double* wb = s_red + (2 * r + 1) * 2 * kGenH8;
+        tp[m - 1] = wa[j] + wb[j];
+        tp[two_bw + m - 1] = wa[kGenH8 + j] + wb[kGenH8 + j];
       }
     }
   }
@@ -754,6 +1179,29 @@ eval_accumulate_narrow_kernel(const double* __restrict__ y, const int64_t* __res
 }
 
 // ------------------------------------------------------------------------------------------
+// Row 0 of W'Y: W's first column is the constant 1, so that row is sum_i y_i per channel -- the
+// same for every candidate.  The tensor-core kernels therefore multiply only the 2 bw sine and
+// cosine rows (40 = five 8-row blocks at bandwidth 20, instead of six for 41) and this small
+// kernel computes the sums once per call, in a fixed order.
+__global__ void __launch_bounds__(1024)
+eval_colsum_kernel(const double* __restrict__ y, int64_t ld_y, int64_t n_indices, int64_t n_chans,
+                   double* __restrict__ colsum) {
+  __shared__ double s_sum[32][33];
+  const int cx = threadIdx.x, ry = threadIdx.y;
+  const int64_t ch = int64_t(blockIdx.x) * 32 + cx;
+  double v = 0.0;
+  if (ch < n_chans)
+    for (int64_t n = ry; n < n_indices; n += 32) v += y[n * ld_y + ch];
+  s_sum[ry][cx] = v;
+  __syncthreads();
+  if (ry == 0 && ch < n_chans) {
+    double total = 0.0;
+    for (int r = 0; r < 32; ++r) total += s_sum[r][cx];
+    colsum[ch] = total;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 constexpr int kSolveThreads = 64;   // one channel per thread in the substitution phase; small, so
                                     // that three CTAs (M = 41) share an SM and hide each other's
                                     // dependent shared-memory chains
@@ -882,8 +1330,12 @@ eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sums
       const double* bp = ws + cand * sh.b_stride_period + ch;
       for (int m = 0; m < M; ++m) {
         double v = 0.0;
-        for (int sp = 0; sp < 2 * sh.n_splits; ++sp)
-          v += bp[sp * sh.b_stride_split + int64_t(m) * sh.n_chans];
+        if (m == 0 && sh.row0_from_colsum) {
+          v = ws[sh.c_offset + ch];  // the constant column of W: the same sum of y for every candidate
+        } else {
+          for (int sp = 0; sp < 2 * sh.n_splits; ++sp)
+            v += bp[sp * sh.b_stride_split + int64_t(m) * sh.n_chans];
+        }
         s_b[m * kSolveThreads + tid] = v;
         s_x[m * kSolveThreads + tid] = v;
       }
@@ -994,6 +1446,8 @@ static int make_shape(int64_t n_chans, int64_t n_indices, int64_t n_periods, int
   sh->t_stride_split = 4 * int64_t(bandwidth);
   sh->t_stride_period = sh->n_splits * sh->t_stride_split;
   sh->t_offset = n_periods * sh->b_stride_period;
+  sh->c_offset = sh->t_offset + n_periods * sh->t_stride_period;
+  sh->row0_from_colsum = 0;
   return PARRM_OK;
 }
 
@@ -1006,7 +1460,7 @@ size_t parrm_eval_workspace_bytes(int64_t n_chans, int64_t n_indices, int64_t n_
   if (n_chans <= 0 || n_indices <= 0 || n_periods <= 0 || bandwidth < 0) return 0;
   parrm::EvalShape sh;
   parrm::make_shape(n_chans, n_indices, n_periods, bandwidth, n_chans, &sh);
-  return size_t(sh.t_offset + n_periods * sh.t_stride_period + 2) * sizeof(double);
+  return size_t(sh.c_offset + n_chans + 2) * sizeof(double);
 }
 
 int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
@@ -1048,6 +1502,32 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
     else
       eval_accumulate_narrow_kernel<2><<<narrow_grid, kNarrowThreads, 0, s>>>(d_y, d_indices,
                                                                               d_periods, ws, sh);
+  } else if (getenv("PARRM_EVAL_SOLO") && *getenv("PARRM_EVAL_SOLO") == '1') {
+    sh.row0_from_colsum = 1;
+    eval_colsum_kernel<<<unsigned(ceil_div(n_chans, 32)), dim3(32, 32), 0, s>>>(
+        d_y, ld_y, n_indices, n_chans, ws + sh.c_offset);
+    const size_t smem =
+        size_t(kSoloBatch * 16 + (kSoloWtTile + 2 * kSoloYTile + 16 * 2 * kGenH8) * sizeof(double));
+    void (*solo)(const double*, const int64_t*, const double*, double*, const EvalShape) = nullptr;
+    switch ((sh.n_rows - 1 + 7) / 8) {
+      case 0: case 1: solo = eval_accumulate_solo_kernel<1>; break;
+      case 2: solo = eval_accumulate_solo_kernel<2>; break;
+      case 3: solo = eval_accumulate_solo_kernel<3>; break;
+      case 4: solo = eval_accumulate_solo_kernel<4>; break;
+      case 5: solo = eval_accumulate_solo_kernel<5>; break;
+      default: solo = eval_accumulate_solo_kernel<6>; break;
+    }
+    PARRM_CUDA_OK(cudaFuncSetAttribute(solo, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    solo<<<grid, kSoloThreads, smem, s>>>(d_y, d_indices, d_periods, ws, sh);
+  } else if (getenv("PARRM_EVAL_TC2") && *getenv("PARRM_EVAL_TC2") == '1') {
+    sh.row0_from_colsum = 1;
+    eval_colsum_kernel<<<unsigned(ceil_div(n_chans, 32)), dim3(32, 32), 0, s>>>(
+        d_y, ld_y, n_indices, n_chans, ws + sh.c_offset);
+    size_t smem = size_t(kSuper * 16 + (kWtTile + 2 * kYTile + 8 * 2 * kHMax) * sizeof(double));
+    if (getenv("PARRM_EVAL_TC2_SOLO")) smem = 120 * 1024;  // experiment: one CTA per SM
+    PARRM_CUDA_OK(cudaFuncSetAttribute(eval_accumulate_tc2_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    eval_accumulate_tc2_kernel<<<grid, kAccThreads, smem, s>>>(d_y, d_indices, d_periods, ws, sh);
   } else if (two_phase && *two_phase == '1') {
     const size_t smem = size_t(kSuper * 16 + (kKT * kRowStride + 2 * kKT * kChanTile + 8 * 2 * kHMax) *
                                                  sizeof(double));
@@ -1055,6 +1535,9 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     eval_accumulate_kernel<<<grid, kAccThreads, smem, s>>>(d_y, d_indices, d_periods, ws, sh);
   } else {
+    sh.row0_from_colsum = 1;
+    eval_colsum_kernel<<<unsigned(ceil_div(n_chans, 32)), dim3(32, 32), 0, s>>>(
+        d_y, ld_y, n_indices, n_chans, ws + sh.c_offset);
     const size_t smem = size_t(64 + kGenThreads * 16 +
                                (kWsStages * (kWtTile + kYTile) + 8 * 2 * kGenH) * sizeof(double));
     PARRM_CUDA_OK(cudaFuncSetAttribute(eval_accumulate_ws_kernel,

@@ -9,7 +9,14 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pyparrm_b200 import _native  # noqa: E402
+
+if os.environ.get("PARRM_TIMING_LIB"):  # alternative build of the library (timing experiments)
+    _native.LIB_PATH = os.environ["PARRM_TIMING_LIB"]
+    _native.lib = _native._load()
 from pyparrm_b200 import _engine  # noqa: E402
+
+_engine.lib = _native.lib
 from pyparrm_b200.synthetic import make_recording  # noqa: E402
 
 n_chans = int(os.environ.get("EVAL_CHANS", "64"))
