@@ -793,6 +793,20 @@ constexpr int kSoloWtStride = 132;        // >= kSoloKT, = 4 (mod 16)
 constexpr int kSoloWtTile = kRowsPad * kSoloWtStride;
 constexpr int kSoloYTile = kSoloKT * kYStride;
 
+#ifdef PARRM_SOLO_TIMING
+// Debug build only: cycles lane 0 of warps 0 (slots 0-7) and 15 (slots 8-15) of CTA (0,0,0)
+// spend in each phase.
+__device__ unsigned long long g_solo_timing[16];
+#define SOLO_TICK(slot)                          \
+  do {                                           \
+    const long long now__ = clock64();           \
+    tacc__[slot] += now__ - tick__;              \
+    tick__ = now__;                              \
+  } while (0)
+#else
+#define SOLO_TICK(slot)
+#endif
+
 template <int N>
 struct IntTag {
   static constexpr int value = N;
@@ -804,8 +818,8 @@ eval_accumulate_solo_kernel(const double* __restrict__ y, const int64_t* __restr
                             const double* __restrict__ periods, double* __restrict__ ws,
                             const EvalShape sh) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2* s_cs = reinterpret_cast<double2*>(smem_raw);                   // [kSoloBatch] (cos, sin)
-  double* s_w = reinterpret_cast<double*>(smem_raw + kSoloBatch * 16);    // [kRowsPad][kSoloWtStride]
+  double2* s_cs = reinterpret_cast<double2*>(smem_raw);  // [4][kSoloBatch] (cos, sin) of z, z^2, z^4, z^8
+  double* s_w = reinterpret_cast<double*>(smem_raw + 4 * kSoloBatch * 16);  // [kRowsPad][kSoloWtStride]
   double* s_y = s_w + kSoloWtTile;                                        // 2 x [kSoloKT][kYStride]
   double* s_red = s_y + 2 * kSoloYTile;                                   // [16 warps][2 * kGenH8]
 
@@ -822,7 +836,7 @@ eval_accumulate_solo_kernel(const double* __restrict__ y, const int64_t* __restr
   const double delta = 6.283185307179586 / periods[cand];  // 2*pi/period (parrm.py:619)
   const bool pair_copies = (sh.ld_y % 2 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
 
-  // generator role: samples gi and gi + 64 of the tile (two independent chains per thread: the
+  // generator role: tile positions gi and gi + 64 (two independent chains per thread: the
   // complex products are latency-bound), residue class r8 -> harmonics r8+1, r8+9, r8+17, ...
   const int gi = tid & 63, r8 = tid >> 6;
   const int h = (two_bw - r8 + 7) / 8;
@@ -845,70 +859,129 @@ eval_accumulate_solo_kernel(const double* __restrict__ y, const int64_t* __restr
 #pragma unroll
     for (int nb = 0; nb < 2; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
 
+  // Tile position p (the k index of the tensor products) holds sample (p % 4) * 32 + p / 4 of
+  // the tile: the four samples of one k-step then come from four 32-sample quarters.  When the
+  // rows of Y are dense (ld_y == channels in use) a quarter is one contiguous 16 KB block, so a
+  // tile arrives in four bulk copies (TMA), issued by one thread a tile ahead, each landing
+  // 32 bytes further round the banks than the one before (the same fragment-load skew that the
+  // padded row stride gives the cp.async form).  Bulk copies must be few and large: one
+  // 512-byte copy per row costs the TMA unit ~57 cycles each (7300 cycles per tile, measured),
+  // and 512 threads issuing 16-byte cp.async stall ~1500 cycles per tile on the L2 -> SM path.
+  __shared__ uint64_t s_full[2];
+  const bool bulk_tiles = pair_copies && gridDim.z == 1 && sh.ld_y == n_chan_here;
+  const int quarter = kSoloKT / 4;                                   // samples per bulk copy
+  const int y_k_stride = bulk_tiles ? quarter * n_chan_here + 4 : kYStride;
+  const int y_step_stride = bulk_tiles ? n_chan_here : 4 * kYStride;
+  if (bulk_tiles) {
+    // rows past the end of the range are never copied: zero everything once so that W = 0
+    // (samples past the end) never meets a non-finite leftover
+    for (int e = tid; e < 2 * kSoloYTile; e += kSoloThreads) s_y[e] = 0.0;
+    if (tid == 0) {
+      mbar_init(&s_full[0], 1);
+      mbar_init(&s_full[1], 1);
+      fence_mbar_init();
+    }
+    fence_proxy_async();
+    __syncthreads();
+  }
   auto stage_y = [&](int buf, int64_t n_tile) {
     double* dst = s_y + buf * kSoloYTile;
-    if (pair_copies) {
+    if (bulk_tiles) {
+      if (tid == 0) {
+        const int rows = int(min64(kSoloKT, n_end - n_tile));
+        const uint32_t row_bytes = uint32_t(n_chan_here) * 8u;
+        mbar_expect_tx(&s_full[buf], uint32_t(rows) * row_bytes);
+        for (int q = 0; q * quarter < rows; ++q)
+          bulk_g2s(dst + q * y_k_stride, y + (n_tile + q * quarter) * sh.ld_y,
+                   uint32_t(min(quarter, rows - q * quarter)) * row_bytes, &s_full[buf]);
+      }
+    } else if (pair_copies) {
       const int c = (tid & 31) * 2, k0 = tid >> 5;
       const bool c_ok = c < n_chan_here;
       for (int k = k0; k < kSoloKT; k += kSoloThreads / 32) {
         const int64_t n = n_tile + k;
         const bool ok = n < n_end && c_ok;
         const int bytes = !ok ? 0 : (c + 1 < n_chan_here ? 16 : 8);
-        cp_async16(dst + k * kYStride + c, ok ? y + n * sh.ld_y + chan0 + c : y, bytes);
+        const int pos = (k % quarter) * 4 + k / quarter;
+        cp_async16(dst + pos * kYStride + c, ok ? y + n * sh.ld_y + chan0 + c : y, bytes);
       }
+      cp_async_commit();
     } else {
       const int c = tid & 63, k0 = tid >> 6;
       for (int k = k0; k < kSoloKT; k += kSoloThreads / 64) {
         const int64_t n = n_tile + k;
         const bool ok = n < n_end && c < n_chan_here;
-        cp_async8(dst + k * kYStride + c, ok ? y + n * sh.ld_y + chan0 + c : y, ok ? 8 : 0);
+        const int pos = (k % quarter) * 4 + k / quarter;
+        cp_async8(dst + pos * kYStride + c, ok ? y + n * sh.ld_y + chan0 + c : y, ok ? 8 : 0);
       }
+      cp_async_commit();
     }
-    cp_async_commit();
   };
   int y_buf = 0;
+  uint32_t y_phase = 0;  // bit b: parity of the next completion of s_full[b]
   if (n_begin < n_end) stage_y(0, n_begin);
+#ifdef PARRM_SOLO_TIMING
+  const bool timed__ = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid == 0 || tid == 480);
+  const int tbase__ = tid == 0 ? 0 : 8;
+  long long tacc__[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tick__ = clock64();
+#endif
 
   for (int64_t n_super = n_begin; n_super < n_end; n_super += kSoloBatch) {
     {  // one accurate sincos per sample of this batch; samples past the end hold z = 0
-      const int64_t n = n_super + tid;
+      // thread = tile position: sample (p % 4) * 32 + p / 4 of tile tid / 128
+      const int p_tile = tid & (kSoloKT - 1);
+      const int64_t n = n_super + (tid - p_tile) + (p_tile & 3) * quarter + (p_tile >> 2);
       double2 cs = make_double2(0.0, 0.0);
       if (n < n_end) {
         const double angle = double(indices[n] + 1) * delta;
         sincos_phase(angle, &cs.y, &cs.x);
       }
+      double2 z2 = cs, z4, z8;
+      cmul(z2.x, z2.y, cs.x, cs.y);
+      z4 = z2;
+      cmul(z4.x, z4.y, z2.x, z2.y);
+      z8 = z4;
+      cmul(z8.x, z8.y, z4.x, z4.y);
       s_cs[tid] = cs;
+      s_cs[kSoloBatch + tid] = z2;
+      s_cs[2 * kSoloBatch + tid] = z4;
+      s_cs[3 * kSoloBatch + tid] = z8;
     }
+    SOLO_TICK(0);
     __syncthreads();
+    SOLO_TICK(1);
     for (int sub = 0; sub < kSoloBatch / kSoloKT; ++sub) {
       const int64_t n_tile = n_super + sub * kSoloKT;
       if (n_tile >= n_end) break;  // uniform
+      // the other Y buffer was last read before the barrier that ended the previous tile
+      if (bulk_tiles && n_tile + kSoloKT < n_end) stage_y(y_buf ^ 1, n_tile + kSoloKT);
+      SOLO_TICK(3);
 #ifndef PARRM_DEBUG_SOLO_NO_GEN
-      {  // ---- generate: class r8 of samples gi, gi + 64 (W transposed, tile row = column - 1) ----
-        const double2 za = s_cs[sub * kSoloKT + gi], zb = s_cs[sub * kSoloKT + gi + 64];
-        double a2c = za.x, a2s = za.y, b2c = zb.x, b2s = zb.y;
-        cmul(a2c, a2s, za.x, za.y);
-        cmul(b2c, b2s, zb.x, zb.y);
-        double a4c = a2c, a4s = a2s, b4c = b2c, b4s = b2s;
-        cmul(a4c, a4s, a2c, a2s);
-        cmul(b4c, b4s, b2c, b2s);
-        double a8c = a4c, a8s = a4s, b8c = b4c, b8s = b4s;
-        cmul(a8c, a8s, a4c, a4s);
-        cmul(b8c, b8s, b4c, b4s);
-        double ca = za.x, sa = za.y, cb = zb.x, sb = zb.y;  // seed z^(r8+1)
-        switch (r8) {
-          case 1: ca = a2c; sa = a2s; cb = b2c; sb = b2s; break;
-          case 2: ca = a2c; sa = a2s; cb = b2c; sb = b2s;
-                  cmul(ca, sa, za.x, za.y); cmul(cb, sb, zb.x, zb.y); break;
-          case 3: ca = a4c; sa = a4s; cb = b4c; sb = b4s; break;
-          case 4: ca = a4c; sa = a4s; cb = b4c; sb = b4s;
-                  cmul(ca, sa, za.x, za.y); cmul(cb, sb, zb.x, zb.y); break;
-          case 5: ca = a4c; sa = a4s; cb = b4c; sb = b4s;
-                  cmul(ca, sa, a2c, a2s); cmul(cb, sb, b2c, b2s); break;
-          case 6: ca = a8c; sa = a8s; cb = b8c; sb = b8s;  // z^8 * conj(z) = z^7 (|z| = 1)
-                  cmul(ca, sa, za.x, -za.y); cmul(cb, sb, zb.x, -zb.y); break;
-          case 7: ca = a8c; sa = a8s; cb = b8c; sb = b8s; break;
-          default: break;
+      {  // ---- generate: class r8 of positions gi, gi + 64 (W transposed, tile row = column - 1) ----
+        // z, z^2, z^4, z^8 of both samples come from the batch table; seed z^(r8+1) costs at
+        // most one more product
+        const double2* pa = s_cs + sub * kSoloKT + gi;
+        const double2* pb = pa + 64;
+        const double2 a8 = pa[3 * kSoloBatch], b8 = pb[3 * kSoloBatch];
+        const double a8c = a8.x, a8s = a8.y, b8c = b8.x, b8s = b8.y;
+        double ca, sa, cb, sb;
+        {
+          // base power and multiplier per class: z^(r8+1) = base * mult
+          //   r8: 0 z | 1 z^2 | 2 z^2 z | 3 z^4 | 4 z^4 z | 5 z^4 z^2 | 6 z^8 conj(z) | 7 z^8
+          const int base = r8 == 0 ? 0 : r8 < 3 ? 1 : r8 < 6 ? 2 : 3;
+          const double2 ba = pa[base * kSoloBatch], bb = pb[base * kSoloBatch];
+          ca = ba.x; sa = ba.y; cb = bb.x; sb = bb.y;
+          if (r8 == 2 || r8 == 4 || r8 == 5 || r8 == 6) {
+            const int mult = r8 == 5 ? 1 : 0;
+            double2 ma = pa[mult * kSoloBatch], mb = pb[mult * kSoloBatch];
+            if (r8 == 6) {  // |z| = 1: z^8 conj(z) = z^7
+              ma.y = -ma.y;
+              mb.y = -mb.y;
+            }
+            cmul(ca, sa, ma.x, ma.y);
+            cmul(cb, sb, mb.x, mb.y);
+          }
         }
         double* wcol = s_w + gi;
         if (r8 == 7)
@@ -933,17 +1006,23 @@ eval_accumulate_solo_kernel(const double* __restrict__ y, const int64_t* __restr
         }
       }
 #endif
-      if (n_tile + kSoloKT < n_end) {  // this tile's Y has been in flight; start the next one
+      SOLO_TICK(2);
+      if (bulk_tiles) {
+        mbar_wait(&s_full[y_buf], (y_phase >> y_buf) & 1u);
+        y_phase ^= 1u << y_buf;
+      } else if (n_tile + kSoloKT < n_end) {  // this tile's Y has been in flight; start the next
         stage_y(y_buf ^ 1, n_tile + kSoloKT);
         cp_async_wait<1>();
       } else {
         cp_async_wait<0>();
       }
+      SOLO_TICK(4);
       __syncthreads();
+      SOLO_TICK(5);
 #ifndef PARRM_DEBUG_SOLO_NO_MMA
       {  // ---- multiply: B += W' Y on the FP64 tensor cores, every warp ----
-        const double* yb =
-            s_y + y_buf * kSoloYTile + (kh * (kSoloKT / 2) + (l & 3)) * kYStride + nq * 16 + (l >> 2);
+        const double* yb = s_y + y_buf * kSoloYTile + (l & 3) * y_k_stride +
+                           kh * (kSoloKT / 8) * y_step_stride + nq * 16 + (l >> 2);
         auto multiply = [&](auto count, int first_block) {
           constexpr int CNT = decltype(count)::value;
           const double* wa =
@@ -953,8 +1032,8 @@ eval_accumulate_solo_kernel(const double* __restrict__ y, const int64_t* __restr
             double a[CNT > 0 ? CNT : 1], b[2];
 #pragma unroll
             for (int mb = 0; mb < CNT; ++mb) a[mb] = wa[mb * 8 * kSoloWtStride + step * 4];
-            b[0] = yb[step * 4 * kYStride];
-            b[1] = yb[step * 4 * kYStride + 8];
+            b[0] = yb[step * y_step_stride];
+            b[1] = yb[step * y_step_stride + 8];
 #pragma unroll
             for (int mb = 0; mb < CNT; ++mb)
 #pragma unroll
@@ -969,11 +1048,17 @@ eval_accumulate_solo_kernel(const double* __restrict__ y, const int64_t* __restr
         else multiply(IntTag<kCnt1>{}, kCnt0);
       }
 #endif
+      SOLO_TICK(6);
       __syncthreads();
+      SOLO_TICK(7);
       y_buf ^= 1;
     }
   }
 
+#ifdef PARRM_SOLO_TIMING
+  if (timed__)
+    for (int i = 0; i < 8; ++i) g_solo_timing[tbase__ + i] += (unsigned long long)tacc__[i];
+#endif
   {  // ---- write the B partial of this (candidate, split, K-half) ----
     double* bp = ws + cand * sh.b_stride_period + (int64_t(split) * 2 + kh) * sh.b_stride_split;
 #pragma unroll
@@ -1454,6 +1539,17 @@ static int make_shape(int64_t n_chans, int64_t n_indices, int64_t n_periods, int
 }  // namespace parrm
 
 extern "C" {
+#ifdef PARRM_SOLO_TIMING
+int parrm_debug_solo_timing(unsigned long long* h_out, int reset) {
+  if (h_out) cudaMemcpyFromSymbol(h_out, parrm::g_solo_timing, sizeof(parrm::g_solo_timing));
+  if (reset) {
+    unsigned long long zero[16] = {0};
+    cudaMemcpyToSymbol(parrm::g_solo_timing, zero, sizeof(zero));
+  }
+  return 0;
+}
+#endif
+
 
 size_t parrm_eval_workspace_bytes(int64_t n_chans, int64_t n_indices, int64_t n_periods,
                                   int bandwidth) {
@@ -1507,7 +1603,7 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
     eval_colsum_kernel<<<unsigned(ceil_div(n_chans, 32)), dim3(32, 32), 0, s>>>(
         d_y, ld_y, n_indices, n_chans, ws + sh.c_offset);
     const size_t smem =
-        size_t(kSoloBatch * 16 + (kSoloWtTile + 2 * kSoloYTile + 16 * 2 * kGenH8) * sizeof(double));
+        size_t(4 * kSoloBatch * 16 + (kSoloWtTile + 2 * kSoloYTile + 16 * 2 * kGenH8) * sizeof(double));
     void (*solo)(const double*, const int64_t*, const double*, double*, const EvalShape) = nullptr;
     switch ((sh.n_rows - 1 + 7) / 8) {
       case 0: case 1: solo = eval_accumulate_solo_kernel<1>; break;
