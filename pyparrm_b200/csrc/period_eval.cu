@@ -15,9 +15,12 @@
 //     exact for any beta (so, like the reference's explicit residual, insensitive to first
 //     order to rounding in the solve).
 // Kernel 1 (accumulate) walks the samples: one accurate sincos(a_i) per sample, harmonics by
-// the angle-addition recurrence in registers, harmonic sums in registers, and a register-tiled
-// FP64 FMA GEMM from shared-memory tiles for B.  Samples can be split over several CTAs per
-// candidate (few candidates, e.g. Nelder-Mead steps); partials are combined in a fixed order.
+// the angle-addition recurrence in registers, harmonic sums in registers, and B from
+// shared-memory tiles -- on the FP64 tensor cores (eval_accumulate_tensor_kernel, the default),
+// by scalar FMAs for one or two channels (eval_accumulate_narrow_kernel), or by a register-tiled
+// scalar-FMA GEMM (eval_accumulate_kernel, the first version, kept as an A/B baseline behind
+// PARRM_EVAL_TWO_PHASE=1).  Samples can be split over several CTAs per candidate (few
+// candidates, e.g. Nelder-Mead steps); partials are combined in a fixed order.
 // Kernel 2 (solve) assembles the Gram matrix, factorises it with partial pivoting (zero pivot
 // -> +inf, the reference's LinAlgError path), solves all channels and reduces the objective.
 #include <stdlib.h>
@@ -70,8 +73,8 @@ __device__ __forceinline__ void cmul(double& c, double& s, double c2, double s2)
 // CUDA's sincos() takes its Payne-Hanek slow path through local memory -- measured as the
 // bottleneck of the whole evaluator.  For |a| < 1e9 a three-term Cody-Waite reduction with
 // FMAs is exact to ~1e-16 rad: q = rint(a * 2/pi) < 2^30, each fma(-q, C_i, r) rounds once, and
-// C1 + C2 + C3 = pi/2 to 5.6e-50.  The reduced argument |r| <= pi/4 then takes sincos()'s fast
-// path and the quadrant is applied by hand.
+// C1 + C2 + C3 = pi/2 to 5.6e-50.  The reduced argument |r| <= pi/4 goes through the polynomial
+// kernels below and the quadrant is applied by hand.
 __device__ __forceinline__ void sincos_phase(double a, double* sn, double* cs) {
   if (!(fabs(a) < 1.0e9)) {
     sincos(a, sn, cs);
@@ -81,8 +84,23 @@ __device__ __forceinline__ void sincos_phase(double a, double* sn, double* cs) {
   double r = fma(-q, 1.5707963267948966, a);
   r = fma(-q, 6.123233995736766e-17, r);
   r = fma(-q, -1.4973849048591698e-33, r);
-  double s, c;
-  sincos(r, &s, &c);
+  // |r| <= pi/4: minimax kernels in z = r^2 (the classic fdlibm k_sin / k_cos coefficients;
+  // plain Horner evaluation is within 1.2e-16 absolute of sin / cos on this interval), two
+  // independent chains instead of sincos()'s own second reduction
+  const double z = r * r;
+  double ps = 1.58969099521155010221e-10, pc = -1.13596475577881948265e-11;
+  ps = fma(ps, z, -2.50507602534068634195e-08);
+  pc = fma(pc, z, 2.08757232129817482790e-09);
+  ps = fma(ps, z, 2.75573137070700676789e-06);
+  pc = fma(pc, z, -2.75573143513906633035e-07);
+  ps = fma(ps, z, -1.98412698298579493134e-04);
+  pc = fma(pc, z, 2.48015872894767294178e-05);
+  ps = fma(ps, z, 8.33333333332248946124e-03);
+  pc = fma(pc, z, -1.38888888888741095749e-03);
+  ps = fma(ps, z, -1.66666666666666324348e-01);
+  pc = fma(pc, z, 4.16666666666666019037e-02);
+  const double s = fma(r * z, ps, r);
+  const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
   const int quadrant = int(static_cast<long long>(q) & 3);
   const double s1 = (quadrant & 1) ? c : s;
   const double c1 = (quadrant & 1) ? s : c;
@@ -301,510 +319,47 @@ eval_accumulate_kernel(const double* __restrict__ y, const int64_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
-// Warp-specialised form of the accumulate kernel (default).  Measured on the two-phase kernel
-// above: the FP64 pipe is 44 % busy, more than half of the samples are FMA warps waiting for
-// their shared-memory operands, and generation, staging and the FMA tiles take turns behind
-// block barriers.  Here 4 generator warps produce tile t + 1 (accurate sincos, harmonic
-// recurrence, W rows, cp.async of the Y rows, harmonic sums in their registers) while 8 FMA
-// warps consume tile t with their operands double-buffered in registers; two mbarrier pairs
-// (full / empty) hand the two shared-memory stages over, so the FMA warps never wait for a
-// block barrier.  Same arithmetic, same workspace layout, one CTA of 384 threads per SM.
-constexpr int kFmaThreads = 256;
-constexpr int kGenThreads = 256;   // 64 sample lanes x 4 harmonic groups
-constexpr int kWsThreads = kFmaThreads + kGenThreads;
-constexpr int kGenGroups = kGenThreads / kKT;
+// Tensor-core form of the accumulate kernel (default for more than two channels): B = W'Y on
+// the FP64 tensor cores (mma.sync m8n8k4, SASS DMMA; tcgen05 has no FP64 kind).
+//
+// One 512-thread CTA per SM alternates between two phases over 128-sample tiles:
+//   generate  all 16 warps produce the tile of W' (residue class mod 8 of the harmonics of two
+//             samples per thread: <= 5 dependent complex products from a table of z, z^2, z^4,
+//             z^8 built once per 512-sample batch), tensor pipe idle;
+//   multiply  all 16 warps issue DMMA only, operands from shared memory.
+// Measured on the two overlapped forms this replaces (generator warps feeding tensor warps
+// through a 3-stage ring, 159.6k candidates/s; two out-of-phase CTAs per SM, slower): a DMMA
+// holds the FP64 pipe of its scheduler partition for 16 cycles and FP64 is one shared pipe, so
+// the generator's dependent scalar FP64 products wait ~10x longer behind tensor work than on an
+// idle pipe -- overlapping the two costs more than it hides.  Y tiles stream in by bulk copy a
+// tile ahead.  The constant row of W'Y (column sums of Y) comes from eval_colsum_kernel, which
+// leaves 2 bw rows = exactly five 8-row blocks at the reference's bandwidth 20.
+constexpr int kGenGroups = 4;   // narrow kernel: harmonic groups (residue classes mod 4) per sample
 constexpr int kGenH = (2 * PARRM_MAX_BANDWIDTH + kGenGroups - 1) / kGenGroups;  // harmonics per group
-constexpr int kTeamThreads = kGenThreads / 2;  // two generator teams produce alternate tiles
 constexpr int kGenH8 = (2 * PARRM_MAX_BANDWIDTH + 7) / 8;  // harmonics per residue class mod 8
-constexpr int kWsStages = 3;
-// Shared-memory tiles of the tensor-core path.  W is stored transposed, [row][sample], Y as
-// [sample][channel]; both with a row stride = 4 (mod 16) doubles, which makes the m8n8k4 fragment
-// loads (lane -> (l % 4, l / 4)) and the generator's stores (lane -> sample) conflict-free.
-constexpr int kWtStride = 68;   // >= kKT
+// Shared-memory tiles.  W is stored transposed, [row][tile position], Y as [sample][channel];
+// row strides = 4 (mod 16) doubles make the m8n8k4 fragment loads (lane -> (l % 4, l / 4)) and
+// the generator's stores (lane -> position) conflict-free.
 constexpr int kYStride = 68;    // >= kChanTile
-constexpr int kWtTile = kRowsPad * kWtStride;
-constexpr int kYTile = kKT * kYStride;
+constexpr int kTensorThreads = 512;
+constexpr int kTensorBatch = kTensorThreads;  // samples per sincos batch (one per thread)
+constexpr int kTensorKT = 128;              // samples per tile: two per thread while generating
+constexpr int kTensorWtStride = 132;        // >= kTensorKT, = 4 (mod 16)
+constexpr int kTensorWtTile = kRowsPad * kTensorWtStride;
+constexpr int kTensorYTile = kTensorKT * kYStride;
 
-__global__ void __launch_bounds__(kWsThreads, 1)
-eval_accumulate_ws_kernel(const double* __restrict__ y, const int64_t* __restrict__ indices,
-                          const double* __restrict__ periods, double* __restrict__ ws,
-                          const EvalShape sh) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);           // [kWsStages]
-  uint64_t* empty = full + kWsStages;                                // [kWsStages]
-  double2* s_cs = reinterpret_cast<double2*>(smem_raw + 64);        // [2 teams][kTeamThreads] (cos, sin)
-  double* s_w = reinterpret_cast<double*>(smem_raw + 64 + kGenThreads * 16);  // stages x [kRowsPad][kWtStride]
-  double* s_y = s_w + kWsStages * kWtTile;                          // stages x [kKT][kYStride]
-  double* s_red = s_y + kWsStages * kYTile;                         // [8 warps][2 * kGenH]
-
-  const int tid = threadIdx.x;
-  const int64_t cand = blockIdx.x;
-  const int split = blockIdx.y;
-  const int ctile = blockIdx.z;
-  const int bw = sh.bandwidth, two_bw = 2 * bw;
-  const int n_rows = sh.n_rows;
-  const int64_t n_begin = int64_t(split) * sh.split_len;
-  const int64_t n_end = min(n_begin + sh.split_len, sh.n_indices);
-  const int chan0 = ctile * kChanTile;
-  const int n_chan_here = int(min64(kChanTile, sh.n_chans - chan0));
-  const int n_tiles = n_end > n_begin ? int((n_end - n_begin + kKT - 1) / kKT) : 0;
-
-  if (tid == 0) {
-    for (int s = 0; s < kWsStages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kFmaThreads / 32);
-    }
-    fence_mbar_init();
-  }
-  __syncthreads();
-  // Tile t lives in stage t % 3; its full / empty barriers complete once per use of the stage,
-  // so the parity a waiter needs follows from t alone (no per-thread phase state).
-
-  if (tid >= kFmaThreads) {
-    // ------------------------------- generator warps -------------------------------
-    // Two teams of 4 warps produce alternate tiles (team = t & 1), each into its own stage, so
-    // the generator's latency -- dependent FP64 chains that queue behind the tensor-core work
-    // on the same pipe -- has two tile times to hide in.  A team thread carries two samples
-    // (gi, gi + 32) of one harmonic group as independent chains.
-    const int gt = tid - kFmaThreads;
-    const int team = gt / kTeamThreads, tt = gt % kTeamThreads;
-    // Harmonics are split into 8 residue classes: class r takes m = r + 1, r + 9, r + 17, ...,
-    // seeded with z^(r+1) and advanced by z^8.  A thread carries classes gg and gg + 4 of two
-    // samples: four independent chains of <= 9 dependent complex products (the generator is
-    // latency-bound: its FP64 instructions queue behind the tensor-core work on the same pipe).
-    const int gi = tt & 31, gg = tt >> 5;
-    const int h0 = (two_bw - gg + 7) / 8, h1 = (two_bw - gg + 3) / 8;  // harmonics per class
-    const double delta = 6.283185307179586 / periods[cand];  // 2*pi/period (parrm.py:619)
-    const bool pair_copies = (sh.ld_y % 2 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
-    double2* cs_team = s_cs + team * kTeamThreads;
-    double sum0_c[kGenH8], sum0_s[kGenH8], sum1_c[kGenH8], sum1_s[kGenH8];
-#pragma unroll
-    for (int j = 0; j < kGenH8; ++j) sum0_c[j] = sum0_s[j] = sum1_c[j] = sum1_s[j] = 0.0;
-    int i = 0;  // index of the tile among this team's tiles
-    for (int t = team; t < n_tiles; t += 2, ++i) {
-      const int s = t % kWsStages;
-      const int64_t n_tile = n_begin + int64_t(t) * kKT;
-      if (t >= kWsStages) mbar_wait(&empty[s], uint32_t(t / kWsStages - 1) & 1u);
-      // Y rows of this tile: asynchronous copies, waited for before the hand-over
-      {
-        double* dst = s_y + s * kYTile;
-        if (pair_copies) {
-          const int c = (tt & 31) * 2, k0 = tt >> 5;  // channel pair, first sample; 4 samples apart
-          const bool c_ok = c < n_chan_here;
-          for (int k = k0; k < kKT; k += kTeamThreads / 32) {
-            const int64_t n = n_tile + k;
-            const bool ok = n < n_end && c_ok;
-            const int bytes = !ok ? 0 : (c + 1 < n_chan_here ? 16 : 8);
-            cp_async16(dst + k * kYStride + c, ok ? y + n * sh.ld_y + chan0 + c : y, bytes);
-          }
-        } else {
-          const int c = tt & 63, k0 = tt >> 6;
-          for (int k = k0; k < kKT; k += kTeamThreads / 64) {
-            const int64_t n = n_tile + k;
-            const bool ok = n < n_end && c < n_chan_here;
-            cp_async8(dst + k * kYStride + c, ok ? y + n * sh.ld_y + chan0 + c : y, ok ? 8 : 0);
-          }
-        }
-        cp_async_commit();
-      }
-      if ((i & 1) == 0) {
-        // one accurate sincos per sample for this tile and the team's next one (t + 2);
-        // invalid lanes hold (0, 0)
-        const int64_t n = n_tile + int64_t(tt >> 6) * 2 * kKT + (tt & 63);
-        double2 cs = make_double2(0.0, 0.0);
-        if (n < n_end) {
-          const double angle = double(indices[n] + 1) * delta;
-          sincos_phase(angle, &cs.y, &cs.x);
-        }
-        cs_team[tt] = cs;
-        named_bar_sync(1 + team, kTeamThreads);
-      }
-      {
-        // samples past the end carry z = 0 (see the sincos batch), so every power, sum and W
-        // entry they produce is zero
-        const double2 za = cs_team[(i & 1) * kKT + gi], zb = cs_team[(i & 1) * kKT + gi + 32];
-        double a2c = za.x, a2s = za.y, b2c = zb.x, b2s = zb.y;  // z^2
-        cmul(a2c, a2s, za.x, za.y);
-        cmul(b2c, b2s, zb.x, zb.y);
-        double a4c = a2c, a4s = a2s, b4c = b2c, b4s = b2s;      // z^4
-        cmul(a4c, a4s, a2c, a2s);
-        cmul(b4c, b4s, b2c, b2s);
-        double a8c = a4c, a8s = a4s, b8c = b4c, b8s = b4s;      // z^8
-        cmul(a8c, a8s, a4c, a4s);
-        cmul(b8c, b8s, b4c, b4s);
-        double ca0 = za.x, sa0 = za.y, cb0 = zb.x, sb0 = zb.y;  // seed z^(gg+1); gg == 0: z
-        if (gg == 1) {
-          ca0 = a2c; sa0 = a2s; cb0 = b2c; sb0 = b2s;
-        } else if (gg == 2) {
-          ca0 = a2c; sa0 = a2s; cb0 = b2c; sb0 = b2s;
-          cmul(ca0, sa0, za.x, za.y);
-          cmul(cb0, sb0, zb.x, zb.y);
-        } else if (gg == 3) {
-          ca0 = a4c; sa0 = a4s; cb0 = b4c; sb0 = b4s;
-        }
-        double ca1 = ca0, sa1 = sa0, cb1 = cb0, sb1 = sb0;      // seed z^(gg+5)
-        cmul(ca1, sa1, a4c, a4s);
-        cmul(cb1, sb1, b4c, b4s);
-        double* wcol = s_w + s * kWtTile + gi;  // wcol[row * kWtStride (+ 32)] = W[sample][row]
-        // tile row r holds column r + 1 of W (the constant column is handled by eval_colsum_kernel)
-        if (gg == kGenGroups - 1)
-          for (int r = n_rows - 1; r < kRowsPad; ++r) wcol[r * kWtStride] = wcol[r * kWtStride + 32] = 0.0;
-#pragma unroll
-        for (int j = 0; j < kGenH8; ++j) {
-          if (j >= h0) break;  // uniform within a warp (h1 <= h0)
-          if (j > 0) {
-            cmul(ca0, sa0, a8c, a8s);
-            cmul(cb0, sb0, b8c, b8s);
-            cmul(ca1, sa1, a8c, a8s);
-            cmul(cb1, sb1, b8c, b8s);
-          }
-          const int m_lo = gg + 1 + 8 * j, m_hi = m_lo + 4;
-          sum0_c[j] += ca0 + cb0;
-          sum0_s[j] += sa0 + sb0;
-          if (m_lo <= bw) {  // columns 2m-1 = sin, 2m = cos (parrm.py:622-623)
-            wcol[(2 * m_lo - 2) * kWtStride] = sa0;
-            wcol[(2 * m_lo - 1) * kWtStride] = ca0;
-            wcol[(2 * m_lo - 2) * kWtStride + 32] = sb0;
-            wcol[(2 * m_lo - 1) * kWtStride + 32] = cb0;
-          }
-          if (j < h1) {
-            sum1_c[j] += ca1 + cb1;
-            sum1_s[j] += sa1 + sb1;
-            if (m_hi <= bw) {
-              wcol[(2 * m_hi - 2) * kWtStride] = sa1;
-              wcol[(2 * m_hi - 1) * kWtStride] = ca1;
-              wcol[(2 * m_hi - 2) * kWtStride + 32] = sb1;
-              wcol[(2 * m_hi - 1) * kWtStride + 32] = cb1;
-            }
-          }
-        }
-      }
-      cp_async_wait<0>();
-      named_bar_sync(1 + team, kTeamThreads);  // W and Y rows of every team thread are in place
-      if (tt == 0) mbar_arrive(&full[s]);
-    }
-    // harmonic sums: reduce over the sample lanes and the two teams (channel tile 0 only)
-    if (ctile == 0) {
-      const int warp = gt >> 5, lane = gt & 31;  // warp = team * 4 + gg
-      double* mine = s_red + warp * 4 * kGenH8;  // [class gg: c, s][class gg + 4: c, s]
-#pragma unroll
-      for (int j = 0; j < kGenH8; ++j) {
-        const double c0 = warp_sum(sum0_c[j]), s0 = warp_sum(sum0_s[j]);
-        const double c1 = warp_sum(sum1_c[j]), s1 = warp_sum(sum1_s[j]);
-        if (lane == 0) {
-          mine[j] = c0;
-          mine[kGenH8 + j] = s0;
-          mine[2 * kGenH8 + j] = c1;
-          mine[3 * kGenH8 + j] = s1;
-        }
-      }
-      named_bar_sync(3, kGenThreads);
-      double* tp = ws + sh.t_offset + cand * sh.t_stride_period + int64_t(split) * sh.t_stride_split;
-      for (int e = gt; e < 8 * kGenH8; e += kGenThreads) {
-        const int r = e / kGenH8, j = e % kGenH8;  // residue class, harmonic m = r + 1 + 8 j
-        const int m = r + 1 + 8 * j;
-        if (m <= two_bw) {
-          const int g = r & 3, hi = r >> 2;
-          const double* wa = s_red + g * 4 * kGenH8 + hi * 2 * kGenH8;        // team 0
-          const double* wb = s_red + (g + 4) * 4 * kGenH8 + hi * 2 * kGenH8;  // team 1
-          tp[m - 1] = wa[j] + wb[j];
-          tp[two_bw + m - 1] = wa[kGenH8 + j] + wb[kGenH8 + j];
-        }
-      }
-    }
-    return;
-  }
-
-  // ---------------------------------- FMA warps ----------------------------------
-  // B += W' Y on the FP64 tensor cores (mma.sync m8n8k4, SASS DMMA).  Measured here: DMMA and
-  // vector DFMA have the same peak (37 TFLOP/s) on B200, but the register-tiled DFMA loop
-  // stops at ~40 % of it (three distinct 64-bit register operands per FMA), while one DMMA
-  // performs 256 FMAs from one double per lane.  Warp (kh, nq): samples kh*32..+32 of the tile,
-  // channels 16 nq..+16, all row blocks of 8.
-  const int warp = tid >> 5, l = tid & 31;
-  const int kh = warp >> 2, nq = warp & 3;
-  const int n_mb = (n_rows - 1 + 7) >> 3;  // row blocks in use (<= 6): tile row r = W column r + 1
-  double acc[6][2][2];
-#pragma unroll
-  for (int mb = 0; mb < 6; ++mb)
-#pragma unroll
-    for (int nb = 0; nb < 2; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
-  for (int t = 0; t < n_tiles; ++t) {
-    const int s = t % kWsStages;
-    mbar_wait(&full[s], uint32_t(t / kWsStages) & 1u);
-    // fragment addresses: A[m][k] = W[k][m] -> lane (m = l / 4, k = l % 4); B[k][n] -> (k = l % 4, n = l / 4)
-    const double* wa = s_w + s * kWtTile + (l >> 2) * kWtStride + kh * (kKT / 2) + (l & 3);
-    const double* yb = s_y + s * kYTile + (kh * (kKT / 2) + (l & 3)) * kYStride + nq * 16 + (l >> 2);
-    double a_cur[6], b_cur[2];
-#pragma unroll
-    for (int mb = 0; mb < 6; ++mb) a_cur[mb] = mb < n_mb ? wa[mb * 8 * kWtStride] : 0.0;
-    b_cur[0] = yb[0];
-    b_cur[1] = yb[8];
-#pragma unroll 2
-    for (int step = 0; step < kKT / 8; ++step) {  // 8 k4-steps per K-half
-      double a_nxt[6], b_nxt[2];
-      const bool more = step + 1 < kKT / 8;
-#pragma unroll
-      for (int mb = 0; mb < 6; ++mb)
-        a_nxt[mb] = (more && mb < n_mb) ? wa[mb * 8 * kWtStride + (step + 1) * 4] : 0.0;
-      b_nxt[0] = more ? yb[(step + 1) * 4 * kYStride] : 0.0;
-      b_nxt[1] = more ? yb[(step + 1) * 4 * kYStride + 8] : 0.0;
-#pragma unroll
-      for (int mb = 0; mb < 6; ++mb) {
-        if (mb < n_mb) {
-#pragma unroll
-          for (int nb = 0; nb < 2; ++nb)
-            asm volatile(
-                "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                : "+d"(acc[mb][nb][0]), "+d"(acc[mb][nb][1])
-                : "d"(a_cur[mb]), "d"(b_cur[nb]));
-        }
-      }
-#pragma unroll
-      for (int mb = 0; mb < 6; ++mb) a_cur[mb] = a_nxt[mb];
-      b_cur[0] = b_nxt[0];
-      b_cur[1] = b_nxt[1];
-    }
-    __syncwarp();
-    if (l == 0) mbar_arrive(&empty[s]);
-  }
-  // ---- write the B partial of this (candidate, split, K-half): C fragment lane (row l / 4,
-  // channels 2 (l % 4), +1) ----
-  {
-    double* bp = ws + cand * sh.b_stride_period + (int64_t(split) * 2 + kh) * sh.b_stride_split;
-#pragma unroll
-    for (int mb = 0; mb < 6; ++mb) {
-      const int row = mb * 8 + (l >> 2) + 1;
-      if (row < n_rows) {
-#pragma unroll
-        for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int ch = nq * 16 + nb * 8 + 2 * (l & 3) + j;
-            if (ch < n_chan_here) bp[int64_t(row) * sh.n_chans + chan0 + ch] = acc[mb][nb][j];
-          }
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Two-phase tensor-core form: every warp first generates (harmonics of a 64-sample tile, all
-// 256 threads, throughput-bound) and then multiplies (DMMA); two CTAs per SM run out of phase,
-// so one CTA's generation hides behind the other's tensor work.  Shares the tile layouts of the
-// warp-specialised kernel and the residue-mod-4 harmonic groups.
-__global__ void __launch_bounds__(kAccThreads, 2)
-eval_accumulate_tc2_kernel(const double* __restrict__ y, const int64_t* __restrict__ indices,
-                           const double* __restrict__ periods, double* __restrict__ ws,
-                           const EvalShape sh) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2* s_cs = reinterpret_cast<double2*>(smem_raw);                  // [kSuper] (cos, sin)
-  double* s_w = reinterpret_cast<double*>(smem_raw + kSuper * 16);       // [kRowsPad][kWtStride]
-  double* s_y = s_w + kWtTile;                                           // 2 x [kKT][kYStride]
-  double* s_red = s_y + 2 * kYTile;                                      // [8 warps][2 * kHMax]
-  constexpr int H = kHMax;
-
-  const int tid = threadIdx.x;
-  const int64_t cand = blockIdx.x;
-  const int split = blockIdx.y;
-  const int ctile = blockIdx.z;
-  const int bw = sh.bandwidth, two_bw = 2 * bw;
-  const int n_rows = sh.n_rows;
-  const int64_t n_begin = int64_t(split) * sh.split_len;
-  const int64_t n_end = min(n_begin + sh.split_len, sh.n_indices);
-  const int chan0 = ctile * kChanTile;
-  const int n_chan_here = int(min64(kChanTile, sh.n_chans - chan0));
-  const double delta = 6.283185307179586 / periods[cand];  // 2*pi/period (parrm.py:619)
-  const bool pair_copies = (sh.ld_y % 2 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
-
-  // generator role: sample lane gi, residue group gg -> harmonics gg+1, gg+5, ...
-  const int gi = tid & (kKT - 1), gg = tid / kKT;
-  const int h = (two_bw - gg + kGroups - 1) / kGroups;
-  double sum_c[H], sum_s[H];
-#pragma unroll
-  for (int j = 0; j < H; ++j) sum_c[j] = sum_s[j] = 0.0;
-  // tensor role: warp (kh, nq): samples kh*32..+32 of the tile, channels 16 nq..+16
-  const int warp = tid >> 5, l = tid & 31;
-  const int kh = warp >> 2, nq = warp & 3;
-  const int n_mb = (n_rows - 1 + 7) >> 3;
-  double acc[6][2][2];
-#pragma unroll
-  for (int mb = 0; mb < 6; ++mb)
-#pragma unroll
-    for (int nb = 0; nb < 2; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
-
-  auto stage_y = [&](int buf, int64_t n_tile) {
-    double* dst = s_y + buf * kYTile;
-    if (pair_copies) {
-      const int c = (tid & 31) * 2, k0 = tid >> 5;
-      const bool c_ok = c < n_chan_here;
-      for (int k = k0; k < kKT; k += kAccThreads / 32) {
-        const int64_t n = n_tile + k;
-        const bool ok = n < n_end && c_ok;
-        const int bytes = !ok ? 0 : (c + 1 < n_chan_here ? 16 : 8);
-        cp_async16(dst + k * kYStride + c, ok ? y + n * sh.ld_y + chan0 + c : y, bytes);
-      }
-    } else {
-      const int c = tid & 63, k0 = tid >> 6;
-      for (int k = k0; k < kKT; k += kAccThreads / 64) {
-        const int64_t n = n_tile + k;
-        const bool ok = n < n_end && c < n_chan_here;
-        cp_async8(dst + k * kYStride + c, ok ? y + n * sh.ld_y + chan0 + c : y, ok ? 8 : 0);
-      }
-    }
-    cp_async_commit();
-  };
-  int y_buf = 0;
-  if (n_begin < n_end) stage_y(0, n_begin);
-
-  for (int64_t n_super = n_begin; n_super < n_end; n_super += kSuper) {
-    {  // one accurate sincos per sample of this batch; samples past the end hold z = 0
-      const int64_t n = n_super + tid;
-      double2 cs = make_double2(0.0, 0.0);
-      if (n < n_end) {
-        const double angle = double(indices[n] + 1) * delta;
-        sincos_phase(angle, &cs.y, &cs.x);
-      }
-      s_cs[tid] = cs;
-    }
-    __syncthreads();
-    for (int sub = 0; sub < kSuper / kKT; ++sub) {
-      const int64_t n_tile = n_super + sub * kKT;
-      if (n_tile >= n_end) break;  // uniform
-      {  // ---- generate the harmonics of kKT samples (W stored transposed) ----
-        const double2 z = s_cs[sub * kKT + gi];
-        double z2c = z.x, z2s = z.y;
-        cmul(z2c, z2s, z.x, z.y);
-        double z4c = z2c, z4s = z2s;
-        cmul(z4c, z4s, z2c, z2s);
-        double c = z.x, sn = z.y;  // seed z^(gg+1)
-        if (gg == 1) {
-          c = z2c; sn = z2s;
-        } else if (gg == 2) {
-          c = z2c; sn = z2s;
-          cmul(c, sn, z.x, z.y);
-        } else if (gg == 3) {
-          c = z4c; sn = z4s;
-        }
-        double* wcol = s_w + gi;
-        // tile row r holds column r + 1 of W (the constant column: eval_colsum_kernel)
-        if (gg == kGroups - 1)
-          for (int r = n_rows - 1; r < kRowsPad; ++r) wcol[r * kWtStride] = 0.0;
-#pragma unroll
-        for (int j = 0; j < H; ++j) {
-          if (j >= h) break;  // uniform within a warp
-          if (j > 0) cmul(c, sn, z4c, z4s);
-          const int m = gg + 1 + kGroups * j;
-          sum_c[j] += c;
-          sum_s[j] += sn;
-          if (m <= bw) {  // columns 2m-1 = sin, 2m = cos (parrm.py:622-623)
-            wcol[(2 * m - 2) * kWtStride] = sn;
-            wcol[(2 * m - 1) * kWtStride] = c;
-          }
-        }
-      }
-      if (n_tile + kKT < n_end) {  // this tile's Y has been in flight; start the next one
-        stage_y(y_buf ^ 1, n_tile + kKT);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
-      __syncthreads();
-      {  // ---- B += W' Y on the FP64 tensor cores ----
-        const double* wa = s_w + (l >> 2) * kWtStride + kh * (kKT / 2) + (l & 3);
-        const double* yb = s_y + y_buf * kYTile + (kh * (kKT / 2) + (l & 3)) * kYStride + nq * 16 + (l >> 2);
-#pragma unroll 2
-        for (int step = 0; step < kKT / 8; ++step) {
-          double a[6], b[2];
-#pragma unroll
-          for (int mb = 0; mb < 6; ++mb) a[mb] = mb < n_mb ? wa[mb * 8 * kWtStride + step * 4] : 0.0;
-          b[0] = yb[step * 4 * kYStride];
-          b[1] = yb[step * 4 * kYStride + 8];
-#pragma unroll
-          for (int mb = 0; mb < 6; ++mb) {
-            if (mb < n_mb) {
-#pragma unroll
-              for (int nb = 0; nb < 2; ++nb)
-                asm volatile(
-                    "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                    : "+d"(acc[mb][nb][0]), "+d"(acc[mb][nb][1])
-                    : "d"(a[mb]), "d"(b[nb]));
-            }
-          }
-        }
-      }
-      __syncthreads();
-      y_buf ^= 1;
-    }
-  }
-
-  {  // ---- write the B partial of this (candidate, split, K-half) ----
-    double* bp = ws + cand * sh.b_stride_period + (int64_t(split) * 2 + kh) * sh.b_stride_split;
-#pragma unroll
-    for (int mb = 0; mb < 6; ++mb) {
-      const int row = mb * 8 + (l >> 2) + 1;
-      if (row < n_rows) {
-#pragma unroll
-        for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int ch = nq * 16 + nb * 8 + 2 * (l & 3) + j;
-            if (ch < n_chan_here) bp[int64_t(row) * sh.n_chans + chan0 + ch] = acc[mb][nb][j];
-          }
-      }
-    }
-  }
-  if (ctile == 0) {  // ---- harmonic sums: reduce the kKT sample lanes of each group ----
-#pragma unroll
-    for (int j = 0; j < H; ++j) {
-      const double c = warp_sum(sum_c[j]);
-      const double sn = warp_sum(sum_s[j]);
-      if (l == 0) {
-        s_red[warp * 2 * H + j] = c;
-        s_red[warp * 2 * H + H + j] = sn;
-      }
-    }
-    __syncthreads();
-    double* tp = ws + sh.t_offset + cand * sh.t_stride_period + int64_t(split) * sh.t_stride_split;
-    for (int e = tid; e < kGroups * H; e += kAccThreads) {
-      const int g = e / H, j = e % H;
-      const int m = g + 1 + kGroups * j;
-      if (m <= two_bw) {
-        tp[m - 1] = s_red[(2 * g) * 2 * H + j] + s_red[(2 * g + 1) * 2 * H + j];
-        tp[two_bw + m - 1] = s_red[(2 * g) * 2 * H + H + j] + s_red[(2 * g + 1) * 2 * H + H + j];
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Alternating tensor-core form (default for more than two channels).  Measured on the two
-// overlapped forms above: a DMMA holds the FP64 pipe for 16 cycles, so scalar FP64 instructions
-// of other warps (the generator's dependent complex products) wait ~10x longer behind tensor
-// work than on an idle pipe -- overlapping generation with DMMA costs more than it hides.  Here
-// one 512-thread CTA per SM alternates: all 16 warps generate a 64-sample tile (one residue
-// class mod 8 of one sample per thread: <= 10 dependent complex products, tensor pipe idle),
-// then all 16 warps multiply it (DMMA only).  Y tiles still stream in through cp.async a tile
-// ahead.  Same tile layouts, arithmetic and workspace as the other tensor forms.
-constexpr int kSoloThreads = 512;
-constexpr int kSoloBatch = kSoloThreads;  // samples per sincos batch (one per thread)
-constexpr int kSoloKT = 128;              // samples per tile: two per thread while generating
-constexpr int kSoloWtStride = 132;        // >= kSoloKT, = 4 (mod 16)
-constexpr int kSoloWtTile = kRowsPad * kSoloWtStride;
-constexpr int kSoloYTile = kSoloKT * kYStride;
-
-#ifdef PARRM_SOLO_TIMING
+#ifdef PARRM_TENSOR_TIMING
 // Debug build only: cycles lane 0 of warps 0 (slots 0-7) and 15 (slots 8-15) of CTA (0,0,0)
 // spend in each phase.
-__device__ unsigned long long g_solo_timing[16];
-#define SOLO_TICK(slot)                          \
+__device__ unsigned long long g_tensor_timing[16];
+#define TENSOR_TICK(slot)                          \
   do {                                           \
     const long long now__ = clock64();           \
     tacc__[slot] += now__ - tick__;              \
     tick__ = now__;                              \
   } while (0)
 #else
-#define SOLO_TICK(slot)
+#define TENSOR_TICK(slot)
 #endif
 
 template <int N>
@@ -813,15 +368,15 @@ struct IntTag {
 };
 
 template <int N_MB>  // 8-row blocks of W' in use: ceil(2 bw / 8)
-__global__ void __launch_bounds__(kSoloThreads, 1)
-eval_accumulate_solo_kernel(const double* __restrict__ y, const int64_t* __restrict__ indices,
+__global__ void __launch_bounds__(kTensorThreads, 1)
+eval_accumulate_tensor_kernel(const double* __restrict__ y, const int64_t* __restrict__ indices,
                             const double* __restrict__ periods, double* __restrict__ ws,
                             const EvalShape sh) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2* s_cs = reinterpret_cast<double2*>(smem_raw);  // [4][kSoloBatch] (cos, sin) of z, z^2, z^4, z^8
-  double* s_w = reinterpret_cast<double*>(smem_raw + 4 * kSoloBatch * 16);  // [kRowsPad][kSoloWtStride]
-  double* s_y = s_w + kSoloWtTile;                                        // 2 x [kSoloKT][kYStride]
-  double* s_red = s_y + 2 * kSoloYTile;                                   // [16 warps][2 * kGenH8]
+  double2* s_cs = reinterpret_cast<double2*>(smem_raw);  // [4][kTensorBatch] (cos, sin) of z, z^2, z^4, z^8
+  double* s_w = reinterpret_cast<double*>(smem_raw + 4 * kTensorBatch * 16);  // [kRowsPad][kTensorWtStride]
+  double* s_y = s_w + kTensorWtTile;                                        // 2 x [kTensorKT][kYStride]
+  double* s_red = s_y + 2 * kTensorYTile;                                   // [16 warps][2 * kGenH8]
 
   const int tid = threadIdx.x;
   const int64_t cand = blockIdx.x;
@@ -869,13 +424,13 @@ eval_accumulate_solo_kernel(const double* __restrict__ y, const int64_t* __restr
   // and 512 threads issuing 16-byte cp.async stall ~1500 cycles per tile on the L2 -> SM path.
   __shared__ uint64_t s_full[2];
   const bool bulk_tiles = pair_copies && gridDim.z == 1 && sh.ld_y == n_chan_here;
-  const int quarter = kSoloKT / 4;                                   // samples per bulk copy
+  const int quarter = kTensorKT / 4;                                   // samples per bulk copy
   const int y_k_stride = bulk_tiles ? quarter * n_chan_here + 4 : kYStride;
   const int y_step_stride = bulk_tiles ? n_chan_here : 4 * kYStride;
   if (bulk_tiles) {
     // rows past the end of the range are never copied: zero everything once so that W = 0
     // (samples past the end) never meets a non-finite leftover
-    for (int e = tid; e < 2 * kSoloYTile; e += kSoloThreads) s_y[e] = 0.0;
+    for (int e = tid; e < 2 * kTensorYTile; e += kTensorThreads) s_y[e] = 0.0;
     if (tid == 0) {
       mbar_init(&s_full[0], 1);
       mbar_init(&s_full[1], 1);
@@ -885,20 +440,24 @@ eval_accumulate_solo_kernel(const double* __restrict__ y, const int64_t* __restr
     __syncthreads();
   }
   auto stage_y = [&](int buf, int64_t n_tile) {
-    double* dst = s_y + buf * kSoloYTile;
+    double* dst = s_y + buf * kTensorYTile;
     if (bulk_tiles) {
-      if (tid == 0) {
-        const int rows = int(min64(kSoloKT, n_end - n_tile));
+      // one copy per warp 0..3 (issuing a bulk copy holds the thread ~150 cycles, and every
+      // warp waits for the slowest at the next barrier).  The barrier phase cannot complete
+      // before thread 0's arrive, whichever order the byte counts arrive in.
+      if ((tid & 31) == 0 && tid < 128) {
+        const int q = tid >> 5;
+        const int rows = int(min64(kTensorKT, n_end - n_tile));
         const uint32_t row_bytes = uint32_t(n_chan_here) * 8u;
-        mbar_expect_tx(&s_full[buf], uint32_t(rows) * row_bytes);
-        for (int q = 0; q * quarter < rows; ++q)
+        if (q == 0) mbar_expect_tx(&s_full[buf], uint32_t(rows) * row_bytes);
+        if (q * quarter < rows)
           bulk_g2s(dst + q * y_k_stride, y + (n_tile + q * quarter) * sh.ld_y,
                    uint32_t(min(quarter, rows - q * quarter)) * row_bytes, &s_full[buf]);
       }
     } else if (pair_copies) {
       const int c = (tid & 31) * 2, k0 = tid >> 5;
       const bool c_ok = c < n_chan_here;
-      for (int k = k0; k < kSoloKT; k += kSoloThreads / 32) {
+      for (int k = k0; k < kTensorKT; k += kTensorThreads / 32) {
         const int64_t n = n_tile + k;
         const bool ok = n < n_end && c_ok;
         const int bytes = !ok ? 0 : (c + 1 < n_chan_here ? 16 : 8);
@@ -908,7 +467,7 @@ eval_accumulate_solo_kernel(const double* __restrict__ y, const int64_t* __restr
       cp_async_commit();
     } else {
       const int c = tid & 63, k0 = tid >> 6;
-      for (int k = k0; k < kSoloKT; k += kSoloThreads / 64) {
+      for (int k = k0; k < kTensorKT; k += kTensorThreads / 64) {
         const int64_t n = n_tile + k;
         const bool ok = n < n_end && c < n_chan_here;
         const int pos = (k % quarter) * 4 + k / quarter;
@@ -917,26 +476,34 @@ eval_accumulate_solo_kernel(const double* __restrict__ y, const int64_t* __restr
       cp_async_commit();
     }
   };
+  // rows of W' between the last harmonic and the end of its 8-row block are read by the tensor
+  // products but never generated: zero them once (the first barrier of the loop orders this)
+  for (int e = tid; e < (N_MB * 8 - (n_rows - 1)) * kTensorKT; e += kTensorThreads)
+    s_w[(n_rows - 1 + e / kTensorKT) * kTensorWtStride + e % kTensorKT] = 0.0;
   int y_buf = 0;
   uint32_t y_phase = 0;  // bit b: parity of the next completion of s_full[b]
   if (n_begin < n_end) stage_y(0, n_begin);
-#ifdef PARRM_SOLO_TIMING
+#ifdef PARRM_TENSOR_TIMING
   const bool timed__ = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid == 0 || tid == 480);
   const int tbase__ = tid == 0 ? 0 : 8;
   long long tacc__[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tick__ = clock64();
 #endif
 
-  for (int64_t n_super = n_begin; n_super < n_end; n_super += kSoloBatch) {
+  // thread = tile position: sample (p % 4) * 32 + p / 4 of tile tid / 128 of the batch
+  const int n_mine = (tid & ~(kTensorKT - 1)) + (tid & 3) * quarter + ((tid & (kTensorKT - 1)) >> 2);
+  int64_t index_mine = n_begin + n_mine < n_end ? indices[n_begin + n_mine] : 0;
+
+  for (int64_t n_super = n_begin; n_super < n_end; n_super += kTensorBatch) {
     {  // one accurate sincos per sample of this batch; samples past the end hold z = 0
-      // thread = tile position: sample (p % 4) * 32 + p / 4 of tile tid / 128
-      const int p_tile = tid & (kSoloKT - 1);
-      const int64_t n = n_super + (tid - p_tile) + (p_tile & 3) * quarter + (p_tile >> 2);
+      const int64_t n = n_super + n_mine;
       double2 cs = make_double2(0.0, 0.0);
       if (n < n_end) {
-        const double angle = double(indices[n] + 1) * delta;
+        const double angle = double(index_mine + 1) * delta;
         sincos_phase(angle, &cs.y, &cs.x);
       }
+      // next batch's index now: its L2 latency hides behind four tiles of work
+      if (n + kTensorBatch < n_end) index_mine = indices[n + kTensorBatch];
       double2 z2 = cs, z4, z8;
       cmul(z2.x, z2.y, cs.x, cs.y);
       z4 = z2;
@@ -944,37 +511,37 @@ eval_accumulate_solo_kernel(const double* __restrict__ y, const int64_t* __restr
       z8 = z4;
       cmul(z8.x, z8.y, z4.x, z4.y);
       s_cs[tid] = cs;
-      s_cs[kSoloBatch + tid] = z2;
-      s_cs[2 * kSoloBatch + tid] = z4;
-      s_cs[3 * kSoloBatch + tid] = z8;
+      s_cs[kTensorBatch + tid] = z2;
+      s_cs[2 * kTensorBatch + tid] = z4;
+      s_cs[3 * kTensorBatch + tid] = z8;
     }
-    SOLO_TICK(0);
+    TENSOR_TICK(0);
     __syncthreads();
-    SOLO_TICK(1);
-    for (int sub = 0; sub < kSoloBatch / kSoloKT; ++sub) {
-      const int64_t n_tile = n_super + sub * kSoloKT;
+    TENSOR_TICK(1);
+    for (int sub = 0; sub < kTensorBatch / kTensorKT; ++sub) {
+      const int64_t n_tile = n_super + sub * kTensorKT;
       if (n_tile >= n_end) break;  // uniform
       // the other Y buffer was last read before the barrier that ended the previous tile
-      if (bulk_tiles && n_tile + kSoloKT < n_end) stage_y(y_buf ^ 1, n_tile + kSoloKT);
-      SOLO_TICK(3);
-#ifndef PARRM_DEBUG_SOLO_NO_GEN
+      if (bulk_tiles && n_tile + kTensorKT < n_end) stage_y(y_buf ^ 1, n_tile + kTensorKT);
+      TENSOR_TICK(3);
+#ifndef PARRM_DEBUG_TENSOR_NO_GEN
       {  // ---- generate: class r8 of positions gi, gi + 64 (W transposed, tile row = column - 1) ----
         // z, z^2, z^4, z^8 of both samples come from the batch table; seed z^(r8+1) costs at
         // most one more product
-        const double2* pa = s_cs + sub * kSoloKT + gi;
+        const double2* pa = s_cs + sub * kTensorKT + gi;
         const double2* pb = pa + 64;
-        const double2 a8 = pa[3 * kSoloBatch], b8 = pb[3 * kSoloBatch];
+        const double2 a8 = pa[3 * kTensorBatch], b8 = pb[3 * kTensorBatch];
         const double a8c = a8.x, a8s = a8.y, b8c = b8.x, b8s = b8.y;
         double ca, sa, cb, sb;
         {
           // base power and multiplier per class: z^(r8+1) = base * mult
           //   r8: 0 z | 1 z^2 | 2 z^2 z | 3 z^4 | 4 z^4 z | 5 z^4 z^2 | 6 z^8 conj(z) | 7 z^8
           const int base = r8 == 0 ? 0 : r8 < 3 ? 1 : r8 < 6 ? 2 : 3;
-          const double2 ba = pa[base * kSoloBatch], bb = pb[base * kSoloBatch];
+          const double2 ba = pa[base * kTensorBatch], bb = pb[base * kTensorBatch];
           ca = ba.x; sa = ba.y; cb = bb.x; sb = bb.y;
           if (r8 == 2 || r8 == 4 || r8 == 5 || r8 == 6) {
             const int mult = r8 == 5 ? 1 : 0;
-            double2 ma = pa[mult * kSoloBatch], mb = pb[mult * kSoloBatch];
+            double2 ma = pa[mult * kTensorBatch], mb = pb[mult * kTensorBatch];
             if (r8 == 6) {  // |z| = 1: z^8 conj(z) = z^7
               ma.y = -ma.y;
               mb.y = -mb.y;
@@ -984,9 +551,6 @@ eval_accumulate_solo_kernel(const double* __restrict__ y, const int64_t* __restr
           }
         }
         double* wcol = s_w + gi;
-        if (r8 == 7)
-          for (int r = n_rows - 1; r < kRowsPad; ++r)
-            wcol[r * kSoloWtStride] = wcol[r * kSoloWtStride + 64] = 0.0;
 #pragma unroll
         for (int j = 0; j < kGenH8; ++j) {
           if (j >= h) break;  // uniform within a warp
@@ -998,40 +562,40 @@ eval_accumulate_solo_kernel(const double* __restrict__ y, const int64_t* __restr
           sum_c[j] += ca + cb;
           sum_s[j] += sa + sb;
           if (m <= bw) {  // columns 2m-1 = sin, 2m = cos (parrm.py:622-623)
-            wcol[(2 * m - 2) * kSoloWtStride] = sa;
-            wcol[(2 * m - 1) * kSoloWtStride] = ca;
-            wcol[(2 * m - 2) * kSoloWtStride + 64] = sb;
-            wcol[(2 * m - 1) * kSoloWtStride + 64] = cb;
+            wcol[(2 * m - 2) * kTensorWtStride] = sa;
+            wcol[(2 * m - 1) * kTensorWtStride] = ca;
+            wcol[(2 * m - 2) * kTensorWtStride + 64] = sb;
+            wcol[(2 * m - 1) * kTensorWtStride + 64] = cb;
           }
         }
       }
 #endif
-      SOLO_TICK(2);
+      TENSOR_TICK(2);
       if (bulk_tiles) {
         mbar_wait(&s_full[y_buf], (y_phase >> y_buf) & 1u);
         y_phase ^= 1u << y_buf;
-      } else if (n_tile + kSoloKT < n_end) {  // this tile's Y has been in flight; start the next
-        stage_y(y_buf ^ 1, n_tile + kSoloKT);
+      } else if (n_tile + kTensorKT < n_end) {  // this tile's Y has been in flight; start the next
+        stage_y(y_buf ^ 1, n_tile + kTensorKT);
         cp_async_wait<1>();
       } else {
         cp_async_wait<0>();
       }
-      SOLO_TICK(4);
+      TENSOR_TICK(4);
       __syncthreads();
-      SOLO_TICK(5);
-#ifndef PARRM_DEBUG_SOLO_NO_MMA
+      TENSOR_TICK(5);
+#ifndef PARRM_DEBUG_TENSOR_NO_MMA
       {  // ---- multiply: B += W' Y on the FP64 tensor cores, every warp ----
-        const double* yb = s_y + y_buf * kSoloYTile + (l & 3) * y_k_stride +
-                           kh * (kSoloKT / 8) * y_step_stride + nq * 16 + (l >> 2);
+        const double* yb = s_y + y_buf * kTensorYTile + (l & 3) * y_k_stride +
+                           kh * (kTensorKT / 8) * y_step_stride + nq * 16 + (l >> 2);
         auto multiply = [&](auto count, int first_block) {
           constexpr int CNT = decltype(count)::value;
           const double* wa =
-              s_w + (first_block * 8 + (l >> 2)) * kSoloWtStride + kh * (kSoloKT / 2) + (l & 3);
+              s_w + (first_block * 8 + (l >> 2)) * kTensorWtStride + kh * (kTensorKT / 2) + (l & 3);
 #pragma unroll 2
-          for (int step = 0; step < kSoloKT / 8; ++step) {
+          for (int step = 0; step < kTensorKT / 8; ++step) {
             double a[CNT > 0 ? CNT : 1], b[2];
 #pragma unroll
-            for (int mb = 0; mb < CNT; ++mb) a[mb] = wa[mb * 8 * kSoloWtStride + step * 4];
+            for (int mb = 0; mb < CNT; ++mb) a[mb] = wa[mb * 8 * kTensorWtStride + step * 4];
             b[0] = yb[step * y_step_stride];
             b[1] = yb[step * y_step_stride + 8];
 #pragma unroll
@@ -1048,16 +612,16 @@ eval_accumulate_solo_kernel(const double* __restrict__ y, const int64_t* __restr
         else multiply(IntTag<kCnt1>{}, kCnt0);
       }
 #endif
-      SOLO_TICK(6);
+      TENSOR_TICK(6);
       __syncthreads();
-      SOLO_TICK(7);
+      TENSOR_TICK(7);
       y_buf ^= 1;
     }
   }
 
-#ifdef PARRM_SOLO_TIMING
+#ifdef PARRM_TENSOR_TIMING
   if (timed__)
-    for (int i = 0; i < 8; ++i) g_solo_timing[tbase__ + i] += (unsigned long long)tacc__[i];
+    for (int i = 0; i < 8; ++i) g_tensor_timing[tbase__ + i] += (unsigned long long)tacc__[i];
 #endif
   {  // ---- write the B partial of this (candidate, split, K-half) ----
     double* bp = ws + cand * sh.b_stride_period + (int64_t(split) * 2 + kh) * sh.b_stride_split;
@@ -1087,7 +651,7 @@ eval_accumulate_solo_kernel(const double* __restrict__ y, const int64_t* __restr
     }
     __syncthreads();
     double* tp = ws + sh.t_offset + cand * sh.t_stride_period + int64_t(split) * sh.t_stride_split;
-    for (int e = tid; e < 8 * kGenH8; e += kSoloThreads) {
+    for (int e = tid; e < 8 * kGenH8; e += kTensorThreads) {
       const int r = e / kGenH8, j = e % kGenH8;
       const int m = r + 1 + 8 * j;
       if (m <= two_bw) {
@@ -1539,12 +1103,12 @@ static int make_shape(int64_t n_chans, int64_t n_indices, int64_t n_periods, int
 }  // namespace parrm
 
 extern "C" {
-#ifdef PARRM_SOLO_TIMING
-int parrm_debug_solo_timing(unsigned long long* h_out, int reset) {
-  if (h_out) cudaMemcpyFromSymbol(h_out, parrm::g_solo_timing, sizeof(parrm::g_solo_timing));
+#ifdef PARRM_TENSOR_TIMING
+int parrm_debug_tensor_timing(unsigned long long* h_out, int reset) {
+  if (h_out) cudaMemcpyFromSymbol(h_out, parrm::g_tensor_timing, sizeof(parrm::g_tensor_timing));
   if (reset) {
     unsigned long long zero[16] = {0};
-    cudaMemcpyToSymbol(parrm::g_solo_timing, zero, sizeof(zero));
+    cudaMemcpyToSymbol(parrm::g_tensor_timing, zero, sizeof(zero));
   }
   return 0;
 }
@@ -1598,33 +1162,7 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
     else
       eval_accumulate_narrow_kernel<2><<<narrow_grid, kNarrowThreads, 0, s>>>(d_y, d_indices,
                                                                               d_periods, ws, sh);
-  } else if (getenv("PARRM_EVAL_SOLO") && *getenv("PARRM_EVAL_SOLO") == '1') {
-    sh.row0_from_colsum = 1;
-    eval_colsum_kernel<<<unsigned(ceil_div(n_chans, 32)), dim3(32, 32), 0, s>>>(
-        d_y, ld_y, n_indices, n_chans, ws + sh.c_offset);
-    const size_t smem =
-        size_t(4 * kSoloBatch * 16 + (kSoloWtTile + 2 * kSoloYTile + 16 * 2 * kGenH8) * sizeof(double));
-    void (*solo)(const double*, const int64_t*, const double*, double*, const EvalShape) = nullptr;
-    switch ((sh.n_rows - 1 + 7) / 8) {
-      case 0: case 1: solo = eval_accumulate_solo_kernel<1>; break;
-      case 2: solo = eval_accumulate_solo_kernel<2>; break;
-      case 3: solo = eval_accumulate_solo_kernel<3>; break;
-      case 4: solo = eval_accumulate_solo_kernel<4>; break;
-      case 5: solo = eval_accumulate_solo_kernel<5>; break;
-      default: solo = eval_accumulate_solo_kernel<6>; break;
-    }
-    PARRM_CUDA_OK(cudaFuncSetAttribute(solo, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    solo<<<grid, kSoloThreads, smem, s>>>(d_y, d_indices, d_periods, ws, sh);
-  } else if (getenv("PARRM_EVAL_TC2") && *getenv("PARRM_EVAL_TC2") == '1') {
-    sh.row0_from_colsum = 1;
-    eval_colsum_kernel<<<unsigned(ceil_div(n_chans, 32)), dim3(32, 32), 0, s>>>(
-        d_y, ld_y, n_indices, n_chans, ws + sh.c_offset);
-    size_t smem = size_t(kSuper * 16 + (kWtTile + 2 * kYTile + 8 * 2 * kHMax) * sizeof(double));
-    if (getenv("PARRM_EVAL_TC2_SOLO")) smem = 120 * 1024;  // experiment: one CTA per SM
-    PARRM_CUDA_OK(cudaFuncSetAttribute(eval_accumulate_tc2_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    eval_accumulate_tc2_kernel<<<grid, kAccThreads, smem, s>>>(d_y, d_indices, d_periods, ws, sh);
-  } else if (two_phase && *two_phase == '1') {
+  } else if (two_phase && *two_phase == '1') {  // scalar-FMA form, kept as an A/B baseline
     const size_t smem = size_t(kSuper * 16 + (kKT * kRowStride + 2 * kKT * kChanTile + 8 * 2 * kHMax) *
                                                  sizeof(double));
     PARRM_CUDA_OK(cudaFuncSetAttribute(eval_accumulate_kernel,
@@ -1634,11 +1172,19 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
     sh.row0_from_colsum = 1;
     eval_colsum_kernel<<<unsigned(ceil_div(n_chans, 32)), dim3(32, 32), 0, s>>>(
         d_y, ld_y, n_indices, n_chans, ws + sh.c_offset);
-    const size_t smem = size_t(64 + kGenThreads * 16 +
-                               (kWsStages * (kWtTile + kYTile) + 8 * 2 * kGenH) * sizeof(double));
-    PARRM_CUDA_OK(cudaFuncSetAttribute(eval_accumulate_ws_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    eval_accumulate_ws_kernel<<<grid, kWsThreads, smem, s>>>(d_y, d_indices, d_periods, ws, sh);
+    const size_t smem =
+        size_t(4 * kTensorBatch * 16 + (kTensorWtTile + 2 * kTensorYTile + 16 * 2 * kGenH8) * sizeof(double));
+    void (*tensor)(const double*, const int64_t*, const double*, double*, const EvalShape) = nullptr;
+    switch ((sh.n_rows - 1 + 7) / 8) {  // 8-row blocks of W' without its constant row
+      case 0: case 1: tensor = eval_accumulate_tensor_kernel<1>; break;
+      case 2: tensor = eval_accumulate_tensor_kernel<2>; break;
+      case 3: tensor = eval_accumulate_tensor_kernel<3>; break;
+      case 4: tensor = eval_accumulate_tensor_kernel<4>; break;
+      case 5: tensor = eval_accumulate_tensor_kernel<5>; break;
+      default: tensor = eval_accumulate_tensor_kernel<6>; break;
+    }
+    PARRM_CUDA_OK(cudaFuncSetAttribute(tensor, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    tensor<<<grid, kTensorThreads, smem, s>>>(d_y, d_indices, d_periods, ws, sh);
   }
   PARRM_LAUNCH_OK("eval_accumulate_kernel");
   const size_t solve_smem =

@@ -52,14 +52,14 @@ print(f"{n_cand} candidates x {len(idx)} samples x {n_chans} ch: {ms:.3f} ms per
       f"{n_cand / ms * 1e3:.0f} cand/s, {ms / n_cand * 1e3:.2f} us per candidate")
 print("clock samples (MHz, W, reasons):", lines[len(lines) // 4], "|", lines[len(lines) // 2], "|", lines[-2])
 
-if hasattr(_native.lib, "parrm_debug_solo_timing"):  # -DPARRM_SOLO_TIMING build: phase split
+if hasattr(_native.lib, "parrm_debug_tensor_timing"):  # -DPARRM_TENSOR_TIMING build: phase split
     import ctypes
 
     buf = (ctypes.c_ulonglong * 16)()
-    _native.lib.parrm_debug_solo_timing(buf, 1)
+    _native.lib.parrm_debug_tensor_timing(buf, 1)
     engine.evaluate_device(tile, d_per, 20, 1.0, n_chans)
     torch.cuda.synchronize()
-    _native.lib.parrm_debug_solo_timing(buf, 0)
+    _native.lib.parrm_debug_tensor_timing(buf, 0)
     names = ["sincos", "sync", "generate", "stage_y", "cp_wait", "sync", "multiply", "sync"]
     tiles = -(-len(idx) // 128)
     for w, base in (("warp 0", 0), ("warp 15", 8)):
