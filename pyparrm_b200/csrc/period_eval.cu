@@ -851,9 +851,11 @@ eval_colsum_kernel(const double* __restrict__ y, int64_t ld_y, int64_t n_indices
 }
 
 // ------------------------------------------------------------------------------------------
-constexpr int kSolveThreads = 64;   // one channel per thread in the substitution phase; small, so
-                                    // that three CTAs (M = 41) share an SM and hide each other's
-                                    // dependent shared-memory chains
+constexpr int kSolveChans = 64;     // channels per pass: one per thread in the substitutions
+constexpr int kSolveThreads = 256;  // ncu on the 64-thread version: ~45k instructions per warp at
+                                    // ~8 cycles each with 6 warps per SM (three CTAs fit by shared
+                                    // memory) -- latency-bound, so the factorisation, the loads
+                                    // and the quadratic form are spread over four times the warps
 constexpr int kGStride = kMaxRows + 1;  // row stride of the Gram matrix
 
 __global__ void __launch_bounds__(kSolveThreads)
@@ -865,8 +867,8 @@ eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sums
   double* s_g0 = s_g + M * kGStride;          // [M][kGStride] Gram matrix, kept unfactored
   double* s_hc = s_g0 + M * kGStride;         // C_0..C_2bw
   double* s_hs = s_hc + kMaxRows;             // S_0..S_2bw
-  double* s_b = s_hs + kMaxRows;              // [M][kSolveThreads] right-hand sides
-  double* s_x = s_b + M * kSolveThreads;      // [M][kSolveThreads] work / solution
+  double* s_b = s_hs + kMaxRows;              // [M][kSolveChans] right-hand sides
+  double* s_x = s_b + M * kSolveChans;        // [M][kSolveChans] work / solution
   __shared__ int s_perm[kMaxRows];
   __shared__ int s_piv;
   __shared__ int s_singular;
@@ -958,26 +960,30 @@ eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sums
     }
     __syncthreads();
     const double inv_p = 1.0 / s_g[k * kGStride + k];
-    for (int i = k + 1 + tid; i < M; i += kSolveThreads) s_g[i * kGStride + k] *= inv_p;
-    __syncthreads();
-    const int rem = M - k - 1;
-    for (int e = tid; e < rem * rem; e += kSolveThreads) {
-      const int i = k + 1 + e / rem, j = k + 1 + e % rem;
-      s_g[i * kGStride + j] =
-          fma(-s_g[i * kGStride + k], s_g[k * kGStride + j], s_g[i * kGStride + j]);
+    // multipliers and trailing update: rows over warps, columns over lanes
+    for (int i = k + 1 + (tid >> 5); i < M; i += kSolveThreads / 32) {
+      const double lik = s_g[i * kGStride + k] * inv_p;
+      __syncwarp();
+      if ((tid & 31) == 0) s_g[i * kGStride + k] = lik;
+      for (int j = k + 1 + (tid & 31); j < M; j += 32)
+        s_g[i * kGStride + j] = fma(-lik, s_g[k * kGStride + j], s_g[i * kGStride + j]);
     }
     __syncthreads();
   }
 
-  // per-channel solve; channels in chunks of kSolveThreads
+  // per-channel solve; channels in passes of kSolveChans.  Thread (lane, role): lane = channel
+  // of the pass; the four roles share the loads and the quadratic form row-wise, role 0 alone
+  // runs the (sequential) substitutions of its channel.
   const double tri = 0.5 * double(M) * double(M + 1);
+  const int lane = tid % kSolveChans, role = tid / kSolveChans;
+  constexpr int kRoles = kSolveThreads / kSolveChans;
   double local = 0.0;
-  for (int64_t c0 = 0; c0 < sh.n_chans; c0 += kSolveThreads) {
-    const int64_t ch = c0 + tid;
+  for (int64_t c0 = 0; c0 < sh.n_chans; c0 += kSolveChans) {
+    const int64_t ch = c0 + lane;
     const bool live = ch < sh.n_chans;
     if (live) {
       const double* bp = ws + cand * sh.b_stride_period + ch;
-      for (int m = 0; m < M; ++m) {
+      for (int m = role; m < M; m += kRoles) {
         double v = 0.0;
         if (m == 0 && sh.row0_from_colsum) {
           v = ws[sh.c_offset + ch];  // the constant column of W: the same sum of y for every candidate
@@ -985,43 +991,58 @@ eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sums
           for (int sp = 0; sp < 2 * sh.n_splits; ++sp)
             v += bp[sp * sh.b_stride_split + int64_t(m) * sh.n_chans];
         }
-        s_b[m * kSolveThreads + tid] = v;
-        s_x[m * kSolveThreads + tid] = v;
+        s_b[m * kSolveChans + lane] = v;
+        s_x[m * kSolveChans + lane] = v;
       }
+    }
+    __syncthreads();
+    // dot products with four independent partial sums: a single FMA chain is bound by the
+    // FP64 latency
+    const double* xt = s_x + lane;
+    auto dot = [&](const double* g_row, int j0, int j1) {
+      double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+      int j = j0;
+      for (; j + 4 <= j1; j += 4) {
+        p0 = fma(g_row[j], xt[j * kSolveChans], p0);
+        p1 = fma(g_row[j + 1], xt[(j + 1) * kSolveChans], p1);
+        p2 = fma(g_row[j + 2], xt[(j + 2) * kSolveChans], p2);
+        p3 = fma(g_row[j + 3], xt[(j + 3) * kSolveChans], p3);
+      }
+      for (; j < j1; ++j) p0 = fma(g_row[j], xt[j * kSolveChans], p0);
+      return (p0 + p1) + (p2 + p3);
+    };
+    if (live && role == 0) {
       // apply the row interchanges, then L (unit lower) and U
       for (int k = 0; k < M; ++k) {
         const int p = s_perm[k];
         if (p != k) {
-          const double t = s_x[k * kSolveThreads + tid];
-          s_x[k * kSolveThreads + tid] = s_x[p * kSolveThreads + tid];
-          s_x[p * kSolveThreads + tid] = t;
+          const double t = s_x[k * kSolveChans + lane];
+          s_x[k * kSolveChans + lane] = s_x[p * kSolveChans + lane];
+          s_x[p * kSolveChans + lane] = t;
         }
       }
-      for (int i = 1; i < M; ++i) {
-        double v = s_x[i * kSolveThreads + tid];
-        for (int j = 0; j < i; ++j) v = fma(-s_g[i * kGStride + j], s_x[j * kSolveThreads + tid], v);
-        s_x[i * kSolveThreads + tid] = v;
-      }
-      for (int i = M - 1; i >= 0; --i) {
-        double v = s_x[i * kSolveThreads + tid];
-        for (int j = i + 1; j < M; ++j)
-          v = fma(-s_g[i * kGStride + j], s_x[j * kSolveThreads + tid], v);
-        s_x[i * kSolveThreads + tid] = v / s_g[i * kGStride + i];
-      }
+      for (int i = 1; i < M; ++i)
+        s_x[i * kSolveChans + lane] -= dot(s_g + i * kGStride, 0, i);
+      for (int i = M - 1; i >= 0; --i)
+        s_x[i * kSolveChans + lane] =
+            (s_x[i * kSolveChans + lane] - dot(s_g + i * kGStride, i + 1, M)) / s_g[i * kGStride + i];
+    }
+    __syncthreads();
+    if (live) {
       // sum_i (y - W beta)^2 = y'y - 2 beta'b + beta'G beta holds for ANY beta, so like the
       // reference's explicit residual (parrm.py:630) it is only second-order sensitive to the
       // rounding of the solve; y'y - beta'b would be first-order sensitive.
       double cross = 0.0, quad = 0.0, penalty = 0.0;
-      for (int m = 0; m < M; ++m) {
-        const double beta = s_x[m * kSolveThreads + tid];
-        double gb = 0.0;
-        for (int j = 0; j < M; ++j) gb = fma(s_g0[m * kGStride + j], s_x[j * kSolveThreads + tid], gb);
-        cross = fma(beta, s_b[m * kSolveThreads + tid], cross);
+      for (int m = role; m < M; m += kRoles) {
+        const double beta = s_x[m * kSolveChans + lane];
+        const double gb = dot(s_g0 + m * kGStride, 0, M);
+        cross = fma(beta, s_b[m * kSolveChans + lane], cross);
         quad = fma(beta, gb, quad);
         penalty = fma((lambda * double(m + 1)) / tri, beta * beta, penalty);
       }
-      local += ((sumsq[ch] - 2.0 * cross) + quad) / double(sh.n_indices) + penalty;
+      local += ((role == 0 ? sumsq[ch] : 0.0) - 2.0 * cross + quad) / double(sh.n_indices) + penalty;
     }
+    __syncthreads();  // the next pass overwrites s_b / s_x
   }
   local = warp_sum(local);
   if ((tid & 31) == 0) s_part[tid >> 5] = local;
@@ -1188,7 +1209,7 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
   }
   PARRM_LAUNCH_OK("eval_accumulate_kernel");
   const size_t solve_smem =
-      size_t(sh.n_rows * (2 * kGStride + 2 * kSolveThreads) + 2 * kMaxRows) * sizeof(double);
+      size_t(sh.n_rows * (2 * kGStride + 2 * kSolveChans) + 2 * kMaxRows) * sizeof(double);
   PARRM_CUDA_OK(cudaFuncSetAttribute(eval_solve_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      int(solve_smem)));
