@@ -59,6 +59,10 @@ struct EvalShape {
   int64_t t_offset;               // start of the harmonic-sum area
   int64_t c_offset;               // start of the per-channel sums of y (row 0 of W'Y)
   int row0_from_colsum;           // 1: the accumulate kernel leaves row 0 to eval_colsum_kernel
+  int64_t y_offset;               // start of the re-tiled copy of Y (tensor kernel, when needed)
+  // what the tensor kernel reads: per channel tile a dense [n_indices][y_row_chans] block
+  int y_row_chans;                // doubles per row (even; the whole row is one channel tile)
+  int64_t y_tile_stride;          // doubles between channel tiles
 };
 
 __device__ __forceinline__ void cmul(double& c, double& s, double c2, double s2) {
@@ -389,7 +393,10 @@ eval_accumulate_tensor_kernel(const double* __restrict__ y, const int64_t* __res
   const int chan0 = ctile * kChanTile;
   const int n_chan_here = int(min64(kChanTile, sh.n_chans - chan0));
   const double delta = 6.283185307179586 / periods[cand];  // 2*pi/period (parrm.py:619)
-  const bool pair_copies = (sh.ld_y % 2 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  // this channel tile of Y: dense rows of row_chans doubles, 16-byte aligned (the caller's array
+  // when it already has that form, else the copy made by eval_retile_kernel)
+  const double* const yt = y + ctile * sh.y_tile_stride;
+  const int row_chans = sh.y_row_chans;
 
   // generator role: tile positions gi and gi + 64 (two independent chains per thread: the
   // complex products are latency-bound), residue class r8 -> harmonics r8+1, r8+9, r8+17, ...
@@ -415,21 +422,19 @@ eval_accumulate_tensor_kernel(const double* __restrict__ y, const int64_t* __res
     for (int nb = 0; nb < 2; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
 
   // Tile position p (the k index of the tensor products) holds sample (p % 4) * 32 + p / 4 of
-  // the tile: the four samples of one k-step then come from four 32-sample quarters.  When the
-  // rows of Y are dense (ld_y == channels in use) a quarter is one contiguous 16 KB block, so a
-  // tile arrives in four bulk copies (TMA), issued by one thread a tile ahead, each landing
-  // 32 bytes further round the banks than the one before (the same fragment-load skew that the
-  // padded row stride gives the cp.async form).  Bulk copies must be few and large: one
-  // 512-byte copy per row costs the TMA unit ~57 cycles each (7300 cycles per tile, measured),
-  // and 512 threads issuing 16-byte cp.async stall ~1500 cycles per tile on the L2 -> SM path.
+  // the tile: the four samples of one k-step then come from four 32-sample quarters.  Rows of
+  // Y are dense, so a quarter is one contiguous block (16 KB at 64 channels) and a tile arrives
+  // in four bulk copies (TMA), issued a tile ahead, each landing 32 bytes further round the
+  // banks than the one before (the fragment-load skew a padded row stride would give).  Bulk
+  // copies must be few and large: one 512-byte copy per row costs the TMA unit ~57 cycles each
+  // (7300 cycles per tile, measured), and 512 threads issuing 16-byte cp.async stall ~1500
+  // cycles per tile on the L2 -> SM path.
   __shared__ uint64_t s_full[2];
-  const bool bulk_tiles = pair_copies && gridDim.z == 1 && sh.ld_y == n_chan_here;
-  const int quarter = kTensorKT / 4;                                   // samples per bulk copy
-  const int y_k_stride = bulk_tiles ? quarter * n_chan_here + 4 : kYStride;
-  const int y_step_stride = bulk_tiles ? n_chan_here : 4 * kYStride;
-  if (bulk_tiles) {
-    // rows past the end of the range are never copied: zero everything once so that W = 0
-    // (samples past the end) never meets a non-finite leftover
+  const int quarter = kTensorKT / 4;  // samples per bulk copy
+  const int y_k_stride = quarter * row_chans + 4;
+  {
+    // rows past the end of the range (and channels past row_chans) are never copied: zero
+    // everything once so that W = 0 (samples past the end) never meets a non-finite leftover
     for (int e = tid; e < 2 * kTensorYTile; e += kTensorThreads) s_y[e] = 0.0;
     if (tid == 0) {
       mbar_init(&s_full[0], 1);
@@ -440,40 +445,18 @@ eval_accumulate_tensor_kernel(const double* __restrict__ y, const int64_t* __res
     __syncthreads();
   }
   auto stage_y = [&](int buf, int64_t n_tile) {
-    double* dst = s_y + buf * kTensorYTile;
-    if (bulk_tiles) {
-      // one copy per warp 0..3 (issuing a bulk copy holds the thread ~150 cycles, and every
-      // warp waits for the slowest at the next barrier).  The barrier phase cannot complete
-      // before thread 0's arrive, whichever order the byte counts arrive in.
-      if ((tid & 31) == 0 && tid < 128) {
-        const int q = tid >> 5;
-        const int rows = int(min64(kTensorKT, n_end - n_tile));
-        const uint32_t row_bytes = uint32_t(n_chan_here) * 8u;
-        if (q == 0) mbar_expect_tx(&s_full[buf], uint32_t(rows) * row_bytes);
-        if (q * quarter < rows)
-          bulk_g2s(dst + q * y_k_stride, y + (n_tile + q * quarter) * sh.ld_y,
-                   uint32_t(min(quarter, rows - q * quarter)) * row_bytes, &s_full[buf]);
-      }
-    } else if (pair_copies) {
-      const int c = (tid & 31) * 2, k0 = tid >> 5;
-      const bool c_ok = c < n_chan_here;
-      for (int k = k0; k < kTensorKT; k += kTensorThreads / 32) {
-        const int64_t n = n_tile + k;
-        const bool ok = n < n_end && c_ok;
-        const int bytes = !ok ? 0 : (c + 1 < n_chan_here ? 16 : 8);
-        const int pos = (k % quarter) * 4 + k / quarter;
-        cp_async16(dst + pos * kYStride + c, ok ? y + n * sh.ld_y + chan0 + c : y, bytes);
-      }
-      cp_async_commit();
-    } else {
-      const int c = tid & 63, k0 = tid >> 6;
-      for (int k = k0; k < kTensorKT; k += kTensorThreads / 64) {
-        const int64_t n = n_tile + k;
-        const bool ok = n < n_end && c < n_chan_here;
-        const int pos = (k % quarter) * 4 + k / quarter;
-        cp_async8(dst + pos * kYStride + c, ok ? y + n * sh.ld_y + chan0 + c : y, ok ? 8 : 0);
-      }
-      cp_async_commit();
+    // one copy per warp 0..3 (issuing a bulk copy holds the thread ~150 cycles, and every warp
+    // waits for the slowest at the next barrier).  The barrier phase cannot complete before
+    // thread 0's arrive, whichever order the byte counts arrive in.
+    if ((tid & 31) == 0 && tid < 128) {
+      double* dst = s_y + buf * kTensorYTile;
+      const int q = tid >> 5;
+      const int rows = int(min64(kTensorKT, n_end - n_tile));
+      const uint32_t row_bytes = uint32_t(row_chans) * 8u;
+      if (q == 0) mbar_expect_tx(&s_full[buf], uint32_t(rows) * row_bytes);
+      if (q * quarter < rows)
+        bulk_g2s(dst + q * y_k_stride, yt + (n_tile + q * quarter) * row_chans,
+                 uint32_t(min(quarter, rows - q * quarter)) * row_bytes, &s_full[buf]);
     }
   };
   // rows of W' between the last harmonic and the end of its 8-row block are read by the tensor
@@ -522,7 +505,7 @@ eval_accumulate_tensor_kernel(const double* __restrict__ y, const int64_t* __res
       const int64_t n_tile = n_super + sub * kTensorKT;
       if (n_tile >= n_end) break;  // uniform
       // the other Y buffer was last read before the barrier that ended the previous tile
-      if (bulk_tiles && n_tile + kTensorKT < n_end) stage_y(y_buf ^ 1, n_tile + kTensorKT);
+      if (n_tile + kTensorKT < n_end) stage_y(y_buf ^ 1, n_tile + kTensorKT);
       TENSOR_TICK(3);
 #ifndef PARRM_DEBUG_TENSOR_NO_GEN
       {  // ---- generate: class r8 of positions gi, gi + 64 (W transposed, tile row = column - 1) ----
@@ -571,22 +554,15 @@ eval_accumulate_tensor_kernel(const double* __restrict__ y, const int64_t* __res
       }
 #endif
       TENSOR_TICK(2);
-      if (bulk_tiles) {
-        mbar_wait(&s_full[y_buf], (y_phase >> y_buf) & 1u);
-        y_phase ^= 1u << y_buf;
-      } else if (n_tile + kTensorKT < n_end) {  // this tile's Y has been in flight; start the next
-        stage_y(y_buf ^ 1, n_tile + kTensorKT);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
+      mbar_wait(&s_full[y_buf], (y_phase >> y_buf) & 1u);
+      y_phase ^= 1u << y_buf;
       TENSOR_TICK(4);
       __syncthreads();
       TENSOR_TICK(5);
 #ifndef PARRM_DEBUG_TENSOR_NO_MMA
       {  // ---- multiply: B += W' Y on the FP64 tensor cores, every warp ----
         const double* yb = s_y + y_buf * kTensorYTile + (l & 3) * y_k_stride +
-                           kh * (kTensorKT / 8) * y_step_stride + nq * 16 + (l >> 2);
+                           kh * (kTensorKT / 8) * row_chans + nq * 16 + (l >> 2);
         auto multiply = [&](auto count, int first_block) {
           constexpr int CNT = decltype(count)::value;
           const double* wa =
@@ -596,8 +572,8 @@ eval_accumulate_tensor_kernel(const double* __restrict__ y, const int64_t* __res
             double a[CNT > 0 ? CNT : 1], b[2];
 #pragma unroll
             for (int mb = 0; mb < CNT; ++mb) a[mb] = wa[mb * 8 * kTensorWtStride + step * 4];
-            b[0] = yb[step * y_step_stride];
-            b[1] = yb[step * y_step_stride + 8];
+            b[0] = yb[step * row_chans];
+            b[1] = yb[step * row_chans + 8];
 #pragma unroll
             for (int mb = 0; mb < CNT; ++mb)
 #pragma unroll
@@ -1055,6 +1031,21 @@ eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sums
   }
 }
 
+// Dense, zero-padded copy of Y per 64-channel tile, [tile][n][64], for the tensor kernel's bulk
+// copies when the caller's array is not already one dense, aligned, even-width tile (more than
+// 64 channels, odd widths, padded rows).  Once per call: 2 x the bytes of Y.
+__global__ void __launch_bounds__(256)
+eval_retile_kernel(const double* __restrict__ y, int64_t ld_y, int64_t n_indices, int64_t n_chans,
+                   int n_chan_tiles, double* __restrict__ out) {
+  const int64_t total = int64_t(n_chan_tiles) * n_indices * kChanTile;
+  for (int64_t e = int64_t(blockIdx.x) * 256 + threadIdx.x; e < total; e += int64_t(gridDim.x) * 256) {
+    const int c = int(e % kChanTile);
+    const int64_t row = (e / kChanTile) % n_indices;
+    const int64_t ch = (e / kChanTile / n_indices) * kChanTile + c;
+    out[e] = ch < n_chans ? y[row * ld_y + ch] : 0.0;
+  }
+}
+
 // first index of the smallest non-NaN value
 __global__ void __launch_bounds__(1024)
 argmin_kernel(const double* __restrict__ v, int64_t n, double* min_value, int64_t* min_index) {
@@ -1118,6 +1109,9 @@ static int make_shape(int64_t n_chans, int64_t n_indices, int64_t n_periods, int
   sh->t_offset = n_periods * sh->b_stride_period;
   sh->c_offset = sh->t_offset + n_periods * sh->t_stride_period;
   sh->row0_from_colsum = 0;
+  sh->y_offset = (sh->c_offset + n_chans + 1) / 2 * 2;  // 16-byte aligned
+  sh->y_row_chans = 0;
+  sh->y_tile_stride = 0;
   return PARRM_OK;
 }
 
@@ -1141,7 +1135,9 @@ size_t parrm_eval_workspace_bytes(int64_t n_chans, int64_t n_indices, int64_t n_
   if (n_chans <= 0 || n_indices <= 0 || n_periods <= 0 || bandwidth < 0) return 0;
   parrm::EvalShape sh;
   parrm::make_shape(n_chans, n_indices, n_periods, bandwidth, n_chans, &sh);
-  return size_t(sh.c_offset + n_chans + 2) * sizeof(double);
+  // the re-tiled copy of Y is only needed by the tensor kernel (more than two channels)
+  const int64_t retile = n_chans > 2 ? int64_t(sh.n_chan_tiles) * n_indices * parrm::kChanTile : 0;
+  return size_t(sh.y_offset + retile + 2) * sizeof(double);
 }
 
 int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
@@ -1195,6 +1191,20 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
         d_y, ld_y, n_indices, n_chans, ws + sh.c_offset);
     const size_t smem =
         size_t(4 * kTensorBatch * 16 + (kTensorWtTile + 2 * kTensorYTile + 16 * 2 * kGenH8) * sizeof(double));
+    const double* y_src = d_y;
+    if (sh.n_chan_tiles == 1 && ld_y == n_chans && n_chans % 2 == 0 &&
+        (reinterpret_cast<uintptr_t>(d_y) & 15) == 0) {
+      sh.y_row_chans = int(n_chans);  // the caller's array is one dense tile already
+      sh.y_tile_stride = 0;
+    } else {
+      double* tiles = ws + sh.y_offset;
+      const int64_t total = int64_t(sh.n_chan_tiles) * n_indices * kChanTile;
+      eval_retile_kernel<<<unsigned(min64(ceil_div(total, 256), 8 * kNumSMs)), 256, 0, s>>>(
+          d_y, ld_y, n_indices, n_chans, sh.n_chan_tiles, tiles);
+      y_src = tiles;
+      sh.y_row_chans = kChanTile;
+      sh.y_tile_stride = n_indices * kChanTile;
+    }
     void (*tensor)(const double*, const int64_t*, const double*, double*, const EvalShape) = nullptr;
     switch ((sh.n_rows - 1 + 7) / 8) {  // 8-row blocks of W' without its constant row
       case 0: case 1: tensor = eval_accumulate_tensor_kernel<1>; break;
@@ -1205,7 +1215,7 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
       default: tensor = eval_accumulate_tensor_kernel<6>; break;
     }
     PARRM_CUDA_OK(cudaFuncSetAttribute(tensor, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    tensor<<<grid, kTensorThreads, smem, s>>>(d_y, d_indices, d_periods, ws, sh);
+    tensor<<<grid, kTensorThreads, smem, s>>>(y_src, d_indices, d_periods, ws, sh);
   }
   PARRM_LAUNCH_OK("eval_accumulate_kernel");
   const size_t solve_smem =
