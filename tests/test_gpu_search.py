@@ -135,6 +135,23 @@ def test_wide_and_narrow_channel_counts(gpu_engine):
         compare_objective(got, want, f"{n_chans} channels", periods, idx, 10)
 
 
+@pytest.mark.parametrize("bandwidth", [1, 4, 7, 12, 16, 23])
+def test_every_row_block_count_and_tile_layout(gpu_engine, bandwidth):
+    """Bandwidths that need 1..6 eight-row blocks of W' (the tensor kernel is compiled per block
+    count), on an odd channel count (re-tiled copy of Y) and a small even one (the caller's
+    array read directly), with a ragged last tile of samples."""
+    base = make_recording(6, 9_000, 2000, 130, seed=17)
+    idx = np.arange(700, 700 + 128 * 9 + 37)
+    periods = 2000 / 130 * (1 + np.array([-1.5e-3, 2e-6, 7e-4]))
+    for n_chans in (3, 6):
+        data = np.ascontiguousarray(base[:n_chans])
+        (tile,) = gpu_engine.prepare_tiles(data, [idx], 3.0)
+        got = gpu_engine.evaluate(tile, periods, bandwidth, 1.0, n_chans)
+        z = oracle.standardise(data, 3.0)
+        want = oracle.objective_many(periods, z, idx, bandwidth, 1.0, n_chans, n_jobs=4)
+        compare_objective(got, want, f"bw {bandwidth}, {n_chans} channels", periods, idx, bandwidth)
+
+
 @pytest.mark.parametrize("name", ["example_dbs", "synthetic_2x30000", "ecog_lfp"])
 def test_find_period_matches_reference(golden, gpu_engine, name):
     g = golden(name)
