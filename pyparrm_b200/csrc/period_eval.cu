@@ -353,9 +353,8 @@ constexpr int kTensorWtTile = kRowsPad * kTensorWtStride;
 constexpr int kTensorYTile = kTensorKT * kYStride;
 
 #ifdef PARRM_TENSOR_TIMING
-// Debug build only: cycles lane 0 of warps 0 (slots 0-7) and 15 (slots 8-15) of CTA (0,0,0)
-// spend in each phase.
-__device__ unsigned long long g_tensor_timing[16];
+// Debug build only: cycles lane 0 of every warp of CTA (0,0,0) spends in each phase.
+__device__ unsigned long long g_tensor_timing[128];  // [warp][phase]
 #define TENSOR_TICK(slot)                          \
   do {                                           \
     const long long now__ = clock64();           \
@@ -400,7 +399,9 @@ eval_accumulate_tensor_kernel(const double* __restrict__ y, const int64_t* __res
 
   // generator role: tile positions gi and gi + 64 (two independent chains per thread: the
   // complex products are latency-bound), residue class r8 -> harmonics r8+1, r8+9, r8+17, ...
-  const int gi = tid & 63, r8 = tid >> 6;
+  // Classes 2, 4, 5, 6 pay one more product for their seed; a class is two warps = two
+  // scheduler partitions (warp % 4), so this order gives every partition two of them
+  const int gi = tid & 63, r8 = (0x71305462 >> (4 * (tid >> 6))) & 7;  // slots 0..7 -> 2 6 4 5 0 3 1 7
   const int h = (two_bw - r8 + 7) / 8;
   double sum_c[kGenH8], sum_s[kGenH8];
 #pragma unroll
@@ -445,12 +446,13 @@ eval_accumulate_tensor_kernel(const double* __restrict__ y, const int64_t* __res
     __syncthreads();
   }
   auto stage_y = [&](int buf, int64_t n_tile) {
-    // one copy per warp 0..3 (issuing a bulk copy holds the thread ~150 cycles, and every warp
-    // waits for the slowest at the next barrier).  The barrier phase cannot complete before
-    // thread 0's arrive, whichever order the byte counts arrive in.
-    if ((tid & 31) == 0 && tid < 128) {
+    // one copy per warp 4..7: issuing a bulk copy holds the thread ~150 cycles, and these warps
+    // own the smaller share of the row blocks, so they leave the multiply phase first.  The
+    // barrier phase cannot complete before the arrive with the byte count, whichever order the
+    // completions arrive in.
+    if ((tid & 31) == 0 && (tid >> 7) == 1) {
       double* dst = s_y + buf * kTensorYTile;
-      const int q = tid >> 5;
+      const int q = (tid >> 5) - 4;
       const int rows = int(min64(kTensorKT, n_end - n_tile));
       const uint32_t row_bytes = uint32_t(row_chans) * 8u;
       if (q == 0) mbar_expect_tx(&s_full[buf], uint32_t(rows) * row_bytes);
@@ -467,8 +469,8 @@ eval_accumulate_tensor_kernel(const double* __restrict__ y, const int64_t* __res
   uint32_t y_phase = 0;  // bit b: parity of the next completion of s_full[b]
   if (n_begin < n_end) stage_y(0, n_begin);
 #ifdef PARRM_TENSOR_TIMING
-  const bool timed__ = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid == 0 || tid == 480);
-  const int tbase__ = tid == 0 ? 0 : 8;
+  const bool timed__ = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid & 31) == 0;
+  const int tbase__ = (tid >> 5) * 8;
   long long tacc__[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tick__ = clock64();
 #endif
@@ -504,8 +506,6 @@ eval_accumulate_tensor_kernel(const double* __restrict__ y, const int64_t* __res
     for (int sub = 0; sub < kTensorBatch / kTensorKT; ++sub) {
       const int64_t n_tile = n_super + sub * kTensorKT;
       if (n_tile >= n_end) break;  // uniform
-      // the other Y buffer was last read before the barrier that ended the previous tile
-      if (n_tile + kTensorKT < n_end) stage_y(y_buf ^ 1, n_tile + kTensorKT);
       TENSOR_TICK(3);
 #ifndef PARRM_DEBUG_TENSOR_NO_GEN
       {  // ---- generate: class r8 of positions gi, gi + 64 (W transposed, tile row = column - 1) ----
@@ -588,6 +588,9 @@ eval_accumulate_tensor_kernel(const double* __restrict__ y, const int64_t* __res
         else multiply(IntTag<kCnt1>{}, kCnt0);
       }
 #endif
+      // next tile's Y: the other buffer was last read before the barrier that ended the previous
+      // tile
+      if (n_tile + kTensorKT < n_end) stage_y(y_buf ^ 1, n_tile + kTensorKT);
       TENSOR_TICK(6);
       __syncthreads();
       TENSOR_TICK(7);
@@ -615,14 +618,14 @@ eval_accumulate_tensor_kernel(const double* __restrict__ y, const int64_t* __res
       }
     }
   }
-  if (ctile == 0) {  // ---- harmonic sums: reduce the kKT sample lanes (2 warps) of each class ----
+  if (ctile == 0) {  // ---- harmonic sums: reduce the 64 position lanes (2 warps) of each class ----
 #pragma unroll
     for (int j = 0; j < kGenH8; ++j) {
       const double c = warp_sum(sum_c[j]);
       const double sn = warp_sum(sum_s[j]);
       if (l == 0) {
-        s_red[warp * 2 * kGenH8 + j] = c;
-        s_red[warp * 2 * kGenH8 + kGenH8 + j] = sn;
+        s_red[(2 * r8 + (warp & 1)) * 2 * kGenH8 + j] = c;
+        s_red[(2 * r8 + (warp & 1)) * 2 * kGenH8 + kGenH8 + j] = sn;
       }
     }
     __syncthreads();
@@ -1122,7 +1125,7 @@ extern "C" {
 int parrm_debug_tensor_timing(unsigned long long* h_out, int reset) {
   if (h_out) cudaMemcpyFromSymbol(h_out, parrm::g_tensor_timing, sizeof(parrm::g_tensor_timing));
   if (reset) {
-    unsigned long long zero[16] = {0};
+    unsigned long long zero[128] = {0};
     cudaMemcpyToSymbol(parrm::g_tensor_timing, zero, sizeof(zero));
   }
   return 0;

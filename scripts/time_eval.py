@@ -55,17 +55,18 @@ print("clock samples (MHz, W, reasons):", lines[len(lines) // 4], "|", lines[len
 if hasattr(_native.lib, "parrm_debug_tensor_timing"):  # -DPARRM_TENSOR_TIMING build: phase split
     import ctypes
 
-    buf = (ctypes.c_ulonglong * 16)()
+    buf = (ctypes.c_ulonglong * 128)()
     _native.lib.parrm_debug_tensor_timing(buf, 1)
     engine.evaluate_device(tile, d_per, 20, 1.0, n_chans)
     torch.cuda.synchronize()
     _native.lib.parrm_debug_tensor_timing(buf, 0)
     names = ["sincos", "sync", "generate", "stage_y", "cp_wait", "sync", "multiply", "sync"]
     tiles = -(-len(idx) // 128)
-    for w, base in (("warp 0", 0), ("warp 15", 8)):
-        vals = [buf[base + i] for i in range(8)]
-        print(w, {n + str(i): round(v / tiles) for i, (n, v) in enumerate(zip(names, vals))},
-              "cycles per 128-sample tile; total", round(sum(vals) / tiles))
+    print("cycles per 128-sample tile, lane 0 of each warp (barrier waits show up in the next phase):")
+    for w in range(16):
+        vals = [buf[w * 8 + i] for i in range(8)]
+        print(f"  warp {w:2d}", {n + str(i): round(v / tiles) for i, (n, v) in enumerate(zip(names, vals))},
+              "total", round(sum(vals) / tiles))
 
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
