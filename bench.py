@@ -129,6 +129,10 @@ def dist_setup(n_gpus: int):
         import torch.distributed as dist
 
         torch.cuda.set_device(local)
+        # before any pinned allocation: keep this rank's host buffers on its GPU's NUMA node
+        from pyparrm_b200._sharding import bind_host_to_gpu
+
+        bind_host_to_gpu(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         return dist, world, rank, local
     torch.cuda.set_device(0)

@@ -42,6 +42,63 @@ def active() -> bool:
     return _enabled
 
 
+def _parse_cpulist(text: str) -> list[int]:
+    """Expand a sysfs CPU list such as ``0-15,64-79``."""
+    cpus: list[int] = []
+    for part in filter(None, text.strip().split(",")):
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def _pci_address(device_index: int) -> str | None:
+    """``dddd:bb:dd.f`` of a CUDA device as sysfs spells it, or None."""
+    import torch
+
+    props = torch.cuda.get_device_properties(device_index)
+    if all(hasattr(props, k) for k in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+        return f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+    try:  # older torch: ask NVML by UUID (robust to CUDA_VISIBLE_DEVICES)
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByUUID(f"GPU-{props.uuid}".encode())
+        bus_id = pynvml.nvmlDeviceGetPciInfo(handle).busId
+        bus_id = bus_id.decode() if isinstance(bus_id, bytes) else bus_id
+        domain, rest = bus_id.lower().split(":", 1)
+        return f"{domain[-4:]}:{rest}"
+    except Exception:  # noqa: BLE001 - topology is optional
+        return None
+
+
+def bind_host_to_gpu(device_index: int) -> list[int]:
+    """Pin this process to the CPUs local to a GPU's PCIe root before it allocates pinned memory.
+
+    With one process per GPU every rank streams its shard through its own pinned ring
+    (``_engine.filter_host``); first-touch then places the ring on the GPU's NUMA node instead
+    of wherever the launcher happened to start the process.  Returns the CPU list used ([] when
+    the topology is not exposed -- nothing is changed then).
+    """
+    import os
+
+    address = _pci_address(device_index)
+    if address is None:
+        return []
+    try:
+        with open(f"/sys/bus/pci/devices/{address}/local_cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+    except (OSError, ValueError):
+        return []
+    allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+    if not allowed:
+        return []
+    try:
+        os.sched_setaffinity(0, allowed)
+    except OSError:
+        return []
+    return allowed
+
+
 def _world_rank():
     import torch.distributed as dist
 

@@ -92,3 +92,10 @@ def test_world_size_two_gloo(tmp_path):
     assert np.all(chan_ok == 1) and np.all(time_ok == 1)
     # each rank evaluated about half of every grid (the Nelder-Mead rounds are replicated)
     assert np.all(calls1 < 0.75 * calls0)
+
+
+def test_cpulist_parsing():
+    from pyparrm_b200._sharding import _parse_cpulist
+
+    assert _parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert _parse_cpulist("") == []
