@@ -31,6 +31,7 @@ namespace parrm {
 
 constexpr int kAccThreads = 256;
 constexpr int kSuper = 256;       // samples per sincos batch (one per thread)
+constexpr int kSplitQuantum = 512;  // sample splits are multiples of every kernel's batch
 constexpr int kKT = 64;           // samples per GEMM tile
 constexpr int kGroups = 4;        // harmonic groups per sample (kGroups * kKT == kAccThreads)
 constexpr int kHMax = (2 * PARRM_MAX_BANDWIDTH + kGroups - 1) / kGroups;  // 12
@@ -49,7 +50,7 @@ struct EvalShape {
   int64_t n_chans, n_indices, n_periods;
   int bandwidth, n_rows;          // n_rows = 2*bw + 1
   int n_splits, n_chan_tiles;
-  int64_t split_len;              // samples per split (multiple of kSuper)
+  int64_t split_len;              // samples per split (multiple of kSplitQuantum)
   int64_t ld_y;
   // workspace layout (doubles)
   int64_t b_stride_split;         // n_rows * n_chans
@@ -811,22 +812,43 @@ eval_accumulate_narrow_kernel(const double* __restrict__ y, const int64_t* __res
 // same for every candidate.  The tensor-core kernels therefore multiply only the 2 bw sine and
 // cosine rows (40 = five 8-row blocks at bandwidth 20, instead of six for 41) and this small
 // kernel computes the sums once per call, in a fixed order.
+// Two stages so that the whole GPU reads Y (a 2-CTA version took 135 us per call, more than the
+// rest of a five-candidate Nelder-Mead round): kColsumBlocks row blocks per 32-channel tile
+// write partial sums, a second small kernel adds them in block order.
+constexpr int kColsumBlocks = 64;
+
 __global__ void __launch_bounds__(1024)
 eval_colsum_kernel(const double* __restrict__ y, int64_t ld_y, int64_t n_indices, int64_t n_chans,
-                   double* __restrict__ colsum) {
+                   double* __restrict__ partial /* [kColsumBlocks][n_chans] */) {
   __shared__ double s_sum[32][33];
   const int cx = threadIdx.x, ry = threadIdx.y;
   const int64_t ch = int64_t(blockIdx.x) * 32 + cx;
+  const int64_t rows = ceil_div(n_indices, kColsumBlocks);
+  const int64_t n0 = int64_t(blockIdx.y) * rows, n1 = min64(n0 + rows, n_indices);
   double v = 0.0;
   if (ch < n_chans)
-    for (int64_t n = ry; n < n_indices; n += 32) v += y[n * ld_y + ch];
+    for (int64_t n = n0 + ry; n < n1; n += 32) v += y[n * ld_y + ch];
   s_sum[ry][cx] = v;
   __syncthreads();
   if (ry == 0 && ch < n_chans) {
     double total = 0.0;
     for (int r = 0; r < 32; ++r) total += s_sum[r][cx];
-    colsum[ch] = total;
+    partial[int64_t(blockIdx.y) * n_chans + ch] = total;
   }
+}
+
+__global__ void __launch_bounds__(256)
+eval_colsum_finish_kernel(const double* __restrict__ partial, int64_t n_chans,
+                          double* __restrict__ colsum) {
+  const int64_t ch = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (ch >= n_chans) return;
+  double t[kColsumBlocks];
+#pragma unroll
+  for (int b = 0; b < kColsumBlocks; ++b) t[b] = partial[int64_t(b) * n_chans + ch];
+  double total = 0.0;
+#pragma unroll
+  for (int b = 0; b < kColsumBlocks; ++b) total += t[b];
+  colsum[ch] = total;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -835,7 +857,8 @@ constexpr int kSolveThreads = 256;  // ncu on the 64-thread version: ~45k instru
                                     // ~8 cycles each with 6 warps per SM (three CTAs fit by shared
                                     // memory) -- latency-bound, so the factorisation, the loads
                                     // and the quadratic form are spread over four times the warps
-constexpr int kGStride = kMaxRows + 1;  // row stride of the Gram matrix
+constexpr int kGStride = kMaxRows + 2;  // row stride of the Gram matrix: odd, so that the pivot
+                                        // search down a column is free of bank conflicts
 
 __global__ void __launch_bounds__(kSolveThreads)
 eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sumsq, double lambda,
@@ -863,7 +886,21 @@ eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sums
       c = double(sh.n_indices);
     } else {
       const double* tp = ws + sh.t_offset + cand * sh.t_stride_period;
-      for (int sp = 0; sp < sh.n_splits; ++sp) {
+      int sp = 0;
+      for (; sp + 4 <= sh.n_splits; sp += 4) {  // fixed order, loads ahead of the adds
+        double tc[4], ts[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          tc[u] = tp[(sp + u) * sh.t_stride_split + e - 1];
+          ts[u] = tp[(sp + u) * sh.t_stride_split + two_bw + e - 1];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          c += tc[u];
+          s += ts[u];
+        }
+      }
+      for (; sp < sh.n_splits; ++sp) {
         c += tp[sp * sh.t_stride_split + e - 1];
         s += tp[sp * sh.t_stride_split + two_bw + e - 1];
       }
@@ -967,8 +1004,18 @@ eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sums
         if (m == 0 && sh.row0_from_colsum) {
           v = ws[sh.c_offset + ch];  // the constant column of W: the same sum of y for every candidate
         } else {
-          for (int sp = 0; sp < 2 * sh.n_splits; ++sp)
-            v += bp[sp * sh.b_stride_split + int64_t(m) * sh.n_chans];
+          // partials in a fixed order, loads eight ahead of the adds (each is an L2 round trip)
+          const double* pm = bp + int64_t(m) * sh.n_chans;
+          const int n_part = 2 * sh.n_splits;
+          int sp = 0;
+          for (; sp + 8 <= n_part; sp += 8) {
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = pm[(sp + u) * sh.b_stride_split];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v += t[u];
+          }
+          for (; sp < n_part; ++sp) v += pm[sp * sh.b_stride_split];
         }
         s_b[m * kSolveChans + lane] = v;
         s_x[m * kSolveChans + lane] = v;
@@ -1098,11 +1145,15 @@ static int make_shape(int64_t n_chans, int64_t n_indices, int64_t n_periods, int
   sh->bandwidth = bandwidth;
   sh->n_rows = 2 * bandwidth + 1;
   sh->n_chan_tiles = int(ceil_div(n_chans, kChanTile));
-  // enough CTAs for ~4 per SM; a split is at least one sincos batch
-  const int64_t want = ceil_div(int64_t(4) * kNumSMs, n_periods * sh->n_chan_tiles);
-  const int64_t max_splits = ceil_div(n_indices, kSuper);
+  // Few candidates (Nelder-Mead rounds): split the samples so that every SM has work -- one
+  // CTA per SM for the tensor kernel, ~4 for the 256-thread kernels.  Every split costs the
+  // solve kernel two more partials to add per row, so no more than that; a split is a whole
+  // number of sincos batches.
+  const int64_t per_sm = n_chans > 2 ? 1 : 4;
+  const int64_t want = ceil_div(per_sm * kNumSMs, n_periods * sh->n_chan_tiles);
+  const int64_t max_splits = ceil_div(n_indices, kSplitQuantum);
   int64_t n_splits = max64(1, min(want, max_splits));
-  sh->split_len = ceil_div(ceil_div(n_indices, n_splits), kSuper) * kSuper;
+  sh->split_len = ceil_div(ceil_div(n_indices, n_splits), kSplitQuantum) * kSplitQuantum;
   sh->n_splits = int(ceil_div(n_indices, sh->split_len));
   sh->ld_y = ld_y;
   sh->b_stride_split = int64_t(sh->n_rows) * n_chans;
@@ -1112,7 +1163,8 @@ static int make_shape(int64_t n_chans, int64_t n_indices, int64_t n_periods, int
   sh->t_offset = n_periods * sh->b_stride_period;
   sh->c_offset = sh->t_offset + n_periods * sh->t_stride_period;
   sh->row0_from_colsum = 0;
-  sh->y_offset = (sh->c_offset + n_chans + 1) / 2 * 2;  // 16-byte aligned
+  // c_offset: n_chans column sums, then kColsumBlocks x n_chans partials
+  sh->y_offset = (sh->c_offset + (1 + kColsumBlocks) * n_chans + 1) / 2 * 2;  // 16-byte aligned
   sh->y_row_chans = 0;
   sh->y_tile_stride = 0;
   return PARRM_OK;
@@ -1190,8 +1242,10 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
     eval_accumulate_kernel<<<grid, kAccThreads, smem, s>>>(d_y, d_indices, d_periods, ws, sh);
   } else {
     sh.row0_from_colsum = 1;
-    eval_colsum_kernel<<<unsigned(ceil_div(n_chans, 32)), dim3(32, 32), 0, s>>>(
-        d_y, ld_y, n_indices, n_chans, ws + sh.c_offset);
+    eval_colsum_kernel<<<dim3(unsigned(ceil_div(n_chans, 32)), kColsumBlocks), dim3(32, 32), 0, s>>>(
+        d_y, ld_y, n_indices, n_chans, ws + sh.c_offset + n_chans);
+    eval_colsum_finish_kernel<<<unsigned(ceil_div(n_chans, 256)), 256, 0, s>>>(
+        ws + sh.c_offset + n_chans, n_chans, ws + sh.c_offset);
     const size_t smem =
         size_t(4 * kTensorBatch * 16 + (kTensorWtTile + 2 * kTensorYTile + 16 * 2 * kGenH8) * sizeof(double));
     const double* y_src = d_y;
