@@ -60,6 +60,7 @@ struct EvalShape {
   int64_t t_offset;               // start of the harmonic-sum area
   int64_t c_offset;               // start of the per-channel sums of y (row 0 of W'Y)
   int row0_from_colsum;           // 1: the accumulate kernel leaves row 0 to eval_colsum_kernel
+  int b_reduced;                  // 1: eval_reduce_partials_kernel has summed the partials of W'Y
   int64_t y_offset;               // start of the re-tiled copy of Y (tensor kernel, when needed)
   // what the tensor kernel reads: per channel tile a dense [n_indices][y_row_chans] block
   int y_row_chans;                // doubles per row (even; the whole row is one channel tile)
@@ -852,6 +853,33 @@ eval_colsum_finish_kernel(const double* __restrict__ partial, int64_t n_chans,
 }
 
 // ------------------------------------------------------------------------------------------
+// Sample splits (few candidates, e.g. a Nelder-Mead round) leave 2 * n_splits partials of W'Y
+// per candidate.  Added up inside the solve kernel they are ~70 dependent L2 round trips on
+// one CTA per candidate (60k of its 235k cycles, measured); here every (candidate, row) gets
+// its own CTA, so the sums cost one short wave.  Fixed order; the total lands in partial 0.
+__global__ void __launch_bounds__(64)
+eval_reduce_partials_kernel(double* __restrict__ ws, const EvalShape sh) {
+  const int64_t cand = blockIdx.x / sh.n_rows;
+  const int m = int(blockIdx.x % sh.n_rows);
+  if (m == 0 && sh.row0_from_colsum) return;  // that row comes from the column sums
+  double* pm = ws + cand * sh.b_stride_period + int64_t(m) * sh.n_chans;
+  const int n_part = 2 * sh.n_splits;
+  for (int64_t ch = threadIdx.x; ch < sh.n_chans; ch += 64) {
+    double v = 0.0;
+    int sp = 0;
+    for (; sp + 8 <= n_part; sp += 8) {
+      double t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = pm[(sp + u) * sh.b_stride_split + ch];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v += t[u];
+    }
+    for (; sp < n_part; ++sp) v += pm[sp * sh.b_stride_split + ch];
+    pm[ch] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 constexpr int kSolveChans = 64;     // channels per pass: one per thread in the substitutions
 constexpr int kSolveThreads = 256;  // ncu on the 64-thread version: ~45k instructions per warp at
                                     // ~8 cycles each with 6 warps per SM (three CTAs fit by shared
@@ -1006,7 +1034,7 @@ eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sums
         } else {
           // partials in a fixed order, loads eight ahead of the adds (each is an L2 round trip)
           const double* pm = bp + int64_t(m) * sh.n_chans;
-          const int n_part = 2 * sh.n_splits;
+          const int n_part = sh.b_reduced ? 1 : 2 * sh.n_splits;
           int sp = 0;
           for (; sp + 8 <= n_part; sp += 8) {
             double t[8];
@@ -1163,6 +1191,7 @@ static int make_shape(int64_t n_chans, int64_t n_indices, int64_t n_periods, int
   sh->t_offset = n_periods * sh->b_stride_period;
   sh->c_offset = sh->t_offset + n_periods * sh->t_stride_period;
   sh->row0_from_colsum = 0;
+  sh->b_reduced = 0;
   // c_offset: n_chans column sums, then kColsumBlocks x n_chans partials
   sh->y_offset = (sh->c_offset + (1 + kColsumBlocks) * n_chans + 1) / 2 * 2;  // 16-byte aligned
   sh->y_row_chans = 0;
@@ -1275,6 +1304,10 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
     tensor<<<grid, kTensorThreads, smem, s>>>(y_src, d_indices, d_periods, ws, sh);
   }
   PARRM_LAUNCH_OK("eval_accumulate_kernel");
+  if (sh.n_splits > 1) {
+    eval_reduce_partials_kernel<<<unsigned(n_periods * sh.n_rows), 64, 0, s>>>(ws, sh);
+    sh.b_reduced = 1;
+  }
   const size_t solve_smem =
       size_t(sh.n_rows * (2 * kGStride + 2 * kSolveChans) + 2 * kMaxRows) * sizeof(double);
   PARRM_CUDA_OK(cudaFuncSetAttribute(eval_solve_kernel,
