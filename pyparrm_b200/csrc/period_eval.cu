@@ -900,6 +900,7 @@ eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sums
   double* s_b = s_hs + kMaxRows;              // [M][kSolveChans] right-hand sides
   double* s_x = s_b + M * kSolveChans;        // [M][kSolveChans] work / solution
   __shared__ int s_perm[kMaxRows];
+  __shared__ double s_inv[kMaxRows];  // reciprocals of the pivots
   __shared__ int s_piv;
   __shared__ int s_singular;
   __shared__ double s_part[kSolveThreads / 32];
@@ -968,21 +969,24 @@ eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sums
   // LU with partial pivoting (row interchanges), in place
   for (int k = 0; k < M; ++k) {
     if (tid < 32) {
-      double best = -1.0;
+      // |v| compared through its bit pattern: for non-negative doubles the unsigned order is
+      // the numeric order, a NaN sorts above infinity (so it wins, like a propagating max), and
+      // integer compares do not wait on the FP64 pipe's latency
+      unsigned long long best = 0ull;
       int best_i = k;
       for (int i = k + tid; i < M; i += 32) {
-        const double v = fabs(s_g[i * kGStride + k]);
-        if (v > best || (v != v && best == best)) {  // NaN wins, like a propagating max
+        const unsigned long long v =
+            static_cast<unsigned long long>(__double_as_longlong(fabs(s_g[i * kGStride + k])));
+        if (v > best) {
           best = v;
           best_i = i;
         }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const unsigned long long ov = __shfl_xor_sync(0xffffffffu, best, o);
         const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-        const bool take = (ov > best) || (ov == best && oi < best_i) || (ov != ov && best == best);
-        if (take) {
+        if (ov > best || (ov == best && oi < best_i)) {
           best = ov;
           best_i = oi;
         }
@@ -990,7 +994,7 @@ eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sums
       if (tid == 0) {
         s_piv = best_i;
         s_perm[k] = best_i;
-        if (best == 0.0) s_singular = 1;
+        if (best == 0ull) s_singular = 1;
       }
     }
     __syncthreads();
@@ -1004,6 +1008,7 @@ eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sums
     }
     __syncthreads();
     const double inv_p = 1.0 / s_g[k * kGStride + k];
+    if (tid == 0) s_inv[k] = inv_p;  // reused by the back substitution
     // multipliers and trailing update: rows over warps, columns over lanes
     for (int i = k + 1 + (tid >> 5); i < M; i += kSolveThreads / 32) {
       const double lik = s_g[i * kGStride + k] * inv_p;
@@ -1079,7 +1084,7 @@ eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sums
         s_x[i * kSolveChans + lane] -= dot(s_g + i * kGStride, 0, i);
       for (int i = M - 1; i >= 0; --i)
         s_x[i * kSolveChans + lane] =
-            (s_x[i * kSolveChans + lane] - dot(s_g + i * kGStride, i + 1, M)) / s_g[i * kGStride + i];
+            (s_x[i * kSolveChans + lane] - dot(s_g + i * kGStride, i + 1, M)) * s_inv[i];
     }
     __syncthreads();
     if (live) {
