@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PARRM_B200_ABI_VERSION 2
+#define PARRM_B200_ABI_VERSION 3
 
 typedef enum {
   PARRM_OK = 0,
@@ -104,6 +104,11 @@ int parrm_standardise_full(const void* d_x, int64_t n_chans, int64_t n_samples, 
  * ---------------------------------------------------------------------- */
 size_t parrm_eval_workspace_bytes(int64_t n_chans, int64_t n_indices, int64_t n_periods,
                                   int bandwidth);
+/* Kernels one parrm_eval_periods call with these arguments enqueues (accumulate + solve, plus
+ * the column-sum pair, the dense copy of y and the partial sums where the shape needs them);
+ * 0 for an empty or invalid shape.  For launch accounting (bench.py's gpu_launches). */
+int parrm_eval_launch_count(const double* d_y, int64_t ld_y, int64_t n_chans, int64_t n_indices,
+                            int64_t n_periods, int bandwidth);
 int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
                        const int64_t* d_indices, int64_t n_chans, int64_t n_indices,
                        const double* d_periods, int64_t n_periods,

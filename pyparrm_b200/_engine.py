@@ -315,7 +315,9 @@ class DeviceEngine:
                     int(n_chans_divisor), _vp(d_err.data_ptr() + 8 * p0),
                     _vp(self._eval_ws.data_ptr()), self._eval_ws.numel(), sp),
                     "parrm_eval_periods")
-                self.launches += 2
+                self.launches += lib.parrm_eval_launch_count(
+                    _vp(tile.y.data_ptr()), tile.n_chans, tile.n_chans, tile.n_indices, p1 - p0,
+                    bandwidth)
             return d_err
 
     def argmin(self, d_values):

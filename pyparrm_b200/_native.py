@@ -19,7 +19,7 @@ F64, F32 = 0, 1
 DIR_BOTH, DIR_PAST, DIR_FUTURE = 0, 1, 2
 DIRECTIONS = {"both": DIR_BOTH, "past": DIR_PAST, "future": DIR_FUTURE}
 MAX_BANDWIDTH = 23
-ABI_VERSION = 2
+ABI_VERSION = 3
 PLAN_AUTO, PLAN_GATHER, PLAN_COMB = 0, 1, 2
 
 # name -> (restype, argtypes); mirrors include/parrm_b200.h one to one
@@ -46,6 +46,7 @@ SIGNATURES = {
          c_void_p],
     ),
     "parrm_eval_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
+    "parrm_eval_launch_count": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int]),
     "parrm_eval_periods": (
         c_int,
         [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int,

@@ -1229,6 +1229,24 @@ size_t parrm_eval_workspace_bytes(int64_t n_chans, int64_t n_indices, int64_t n_
   return size_t(sh.y_offset + retile + 2) * sizeof(double);
 }
 
+static bool y_is_one_dense_tile(const double* d_y, int64_t ld_y, int64_t n_chans) {
+  return n_chans <= parrm::kChanTile && ld_y == n_chans && n_chans % 2 == 0 &&
+         (reinterpret_cast<uintptr_t>(d_y) & 15) == 0;
+}
+
+int parrm_eval_launch_count(const double* d_y, int64_t ld_y, int64_t n_chans, int64_t n_indices,
+                            int64_t n_periods, int bandwidth) {
+  if (n_chans <= 0 || n_indices <= 0 || n_periods <= 0 || bandwidth < 0 ||
+      bandwidth > PARRM_MAX_BANDWIDTH)
+    return 0;
+  parrm::EvalShape sh;
+  parrm::make_shape(n_chans, n_indices, n_periods, bandwidth, ld_y, &sh);
+  int n = 2;  // accumulate + solve
+  if (n_chans > 2) n += 2 + (y_is_one_dense_tile(d_y, ld_y, n_chans) ? 0 : 1);
+  if (sh.n_splits > 1) n += 1;
+  return n;
+}
+
 int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
                        const int64_t* d_indices, int64_t n_chans, int64_t n_indices,
                        const double* d_periods, int64_t n_periods, int bandwidth, double lambda,
@@ -1283,8 +1301,7 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
     const size_t smem =
         size_t(4 * kTensorBatch * 16 + (kTensorWtTile + 2 * kTensorYTile + 16 * 2 * kGenH8) * sizeof(double));
     const double* y_src = d_y;
-    if (sh.n_chan_tiles == 1 && ld_y == n_chans && n_chans % 2 == 0 &&
-        (reinterpret_cast<uintptr_t>(d_y) & 15) == 0) {
+    if (y_is_one_dense_tile(d_y, ld_y, n_chans)) {
       sh.y_row_chans = int(n_chans);  // the caller's array is one dense tile already
       sh.y_tile_stride = 0;
     } else {
