@@ -14,5 +14,13 @@ for variant in SKIP_SLIDE SKIP_GATHER; do
     "$here"/cabi.cu "$here"/taps.cu "$here"/filter.cu "$here"/filter_plan.cu "$here"/standardise.cu \
     "$here"/period_eval.cu -o "$root/build/libparrm_b200_$variant.so" 2>/dev/null &
 done
+# evaluator: phase counters of the tensor kernel (scripts/time_eval.py prints them when
+# PARRM_TIMING_LIB points at this build), and the kernel with one of its phases compiled out
+for variant in TENSOR_TIMING DEBUG_TENSOR_NO_MMA DEBUG_TENSOR_NO_GEN; do
+  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC \
+    -DPARRM_$variant -I"$root/include" -I"$here" -shared -cudart static \
+    "$here"/cabi.cu "$here"/taps.cu "$here"/filter.cu "$here"/filter_plan.cu "$here"/standardise.cu \
+    "$here"/period_eval.cu -o "$root/build/libparrm_b200_$variant.so" 2>/dev/null &
+done
 wait
 echo built debug variants
