@@ -152,6 +152,23 @@ def test_every_row_block_count_and_tile_layout(gpu_engine, bandwidth):
         compare_objective(got, want, f"bw {bandwidth}, {n_chans} channels", periods, idx, bandwidth)
 
 
+@pytest.mark.parametrize("n_fit", [40, 128, 129, 512, 640, 1153])
+def test_short_and_tile_aligned_sample_counts(gpu_engine, n_fit):
+    """Fewer samples than one 128-sample tile, exact tile / batch multiples and one past them,
+    through the tensor kernel (4 channels) and the narrow one (1 channel)."""
+    base = make_recording(4, 6_000, 2000, 130, seed=19)
+    idx = np.arange(300, 300 + n_fit)
+    periods = 2000 / 130 * (1 + np.array([-1e-3, 4e-6, 2e-3, 5e-3]))
+    for n_chans, bandwidth in ((4, 2), (4, 5), (1, 5)):
+        data = np.ascontiguousarray(base[:n_chans])
+        (tile,) = gpu_engine.prepare_tiles(data, [idx], 3.0)
+        got = gpu_engine.evaluate(tile, periods, bandwidth, 1.0, n_chans)
+        z = oracle.standardise(data, 3.0)
+        want = oracle.objective_many(periods, z, idx, bandwidth, 1.0, n_chans, n_jobs=4)
+        compare_objective(got, want, f"N {n_fit}, {n_chans} ch, bw {bandwidth}", periods, idx,
+                          bandwidth)
+
+
 @pytest.mark.parametrize("name", ["example_dbs", "synthetic_2x30000", "ecog_lfp"])
 def test_find_period_matches_reference(golden, gpu_engine, name):
     g = golden(name)
