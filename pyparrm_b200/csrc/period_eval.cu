@@ -569,7 +569,7 @@ eval_accumulate_tensor_kernel(const double* __restrict__ y, const int64_t* __res
           constexpr int CNT = decltype(count)::value;
           const double* wa =
               s_w + (first_block * 8 + (l >> 2)) * kTensorWtStride + kh * (kTensorKT / 2) + (l & 3);
-#pragma unroll 2
+#pragma unroll
           for (int step = 0; step < kTensorKT / 8; ++step) {
             double a[CNT > 0 ? CNT : 1], b[2];
 #pragma unroll
