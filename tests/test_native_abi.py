@@ -46,6 +46,23 @@ def test_argument_errors_are_reported_not_crashed():
     assert _native.lib.parrm_filter_plan_bytes(160) >= 32 + 160 * 4
 
 
+def test_launch_accounting_follows_the_shape():
+    """parrm_eval_launch_count is host arithmetic: accumulate + solve, the column-sum pair of
+    the tensor path, the dense copy of y for wide / odd layouts, the partial sums of split
+    launches."""
+    count = _native.lib.parrm_eval_launch_count
+    n = 24_000
+    assert count(None, 64, 64, n, 3048, 20) == 4      # one dense tile, one CTA per candidate
+    assert count(None, 64, 64, n, 5, 20) == 5         # few candidates: sample splits
+    assert count(None, 256, 256, n, 3048, 20) == 5    # four channel tiles: re-tiled copy
+    assert count(None, 7, 7, n, 3048, 20) == 5        # odd width: re-tiled copy
+    assert count(None, 80, 64, n, 3048, 20) == 5      # padded rows: re-tiled copy
+    assert count(None, 1, 1, n, 100_000, 20) == 2     # narrow kernel
+    assert count(None, 1, 1, n, 3, 20) == 3
+    assert count(None, 64, 64, n, 0, 20) == 0
+    assert count(None, 64, 64, n, 10, 99) == 0
+
+
 def test_no_silent_cpu_path():
     import torch
 
