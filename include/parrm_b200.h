@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PARRM_B200_ABI_VERSION 3
+#define PARRM_B200_ABI_VERSION 4
 
 typedef enum {
   PARRM_OK = 0,
@@ -165,6 +165,44 @@ int parrm_filter_apply(const void* d_x, int64_t ld_x, int64_t x_t0, int64_t n_x,
                        int64_t n_samples_total, int64_t n_chans,
                        const void* d_plan, const void* h_plan,
                        int dtype, void* stream);
+
+/* Which kernel evaluates the plan.  AUTO picks, for comb plans, a kernel SPECIALISED for the
+ * plan at run time (NVRTC, sm_100a: stride, box lengths and tap offsets are immediates; built
+ * once per plan and device, about a second) when the call is large enough to be worth it or
+ * the kernel already exists, else the pre-built STRIP kernels, else the GATHER.  All of them
+ * compute the same tap sum; they differ in floating-point association only. */
+typedef enum {
+  PARRM_FILTER_KERNEL_AUTO = 0,
+  PARRM_FILTER_KERNEL_GATHER = 1,
+  PARRM_FILTER_KERNEL_STRIP = 2,
+  PARRM_FILTER_KERNEL_SPECIALISED = 3
+} parrm_filter_kernel_t;
+
+/* Launch options of parrm_filter_apply_ex (all zero = library defaults; NULL allowed). */
+typedef struct {
+  int32_t kernel;           /* parrm_filter_kernel_t */
+  int32_t steps_per_chunk;  /* specialised kernel: comb steps per TMA chunk */
+  int32_t prefetch_chunks;  /* specialised kernel: chunks in flight beyond the tap window */
+  int32_t ctas_per_sm;      /* specialised kernel: resident CTAs per SM (1 or 2) */
+  int32_t reserved[4];
+} parrm_filter_options_t;
+
+int parrm_filter_apply_ex(const void* d_x, int64_t ld_x, int64_t x_t0, int64_t n_x,
+                          void* d_out, int64_t ld_out, int64_t t0, int64_t n_out,
+                          int64_t n_samples_total, int64_t n_chans,
+                          const void* d_plan, const void* h_plan,
+                          int dtype, const parrm_filter_options_t* options, void* stream);
+/* Name of the kernel the calling thread's last parrm_filter_apply* enqueued ("" before the
+ * first call): tests and bench.py assert on it so that a fallback is never silent. */
+const char* parrm_filter_last_kernel(void);
+/* Builds the specialised kernel for a plan WITHOUT loading or launching it (works on a host
+ * with no GPU): the build check of the run-time compiled path.  shape[0..11] (may be NULL) =
+ * stride, box kinds, M0, M1, boxes of M0, boxes of M1, single taps, steps per chunk, chunks
+ * in flight, CTAs per SM, dynamic shared memory bytes, threads per CTA.
+ * PARRM_ERR_UNSUPPORTED: plan outside the kernel's range, or NVRTC not available. */
+int parrm_filter_specialise_check(const void* h_plan, int dtype,
+                                  const parrm_filter_options_t* options, int32_t* shape,
+                                  size_t* cubin_bytes);
 
 /* Element-wise precision conversion for the float32 storage mode of the filter (the recording
  * crosses PCIe as float64, as the reference's API hands it over, parrm.py:866-875). */

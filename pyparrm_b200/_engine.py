@@ -105,6 +105,7 @@ class DeviceEngine:
         self._eval_ws = None
         self._plans: dict = {}
         self.launches = 0          # kernels of ours enqueued (bench.py reports it)
+        self.last_filter_kernel = ""
 
     # ------------------------------------------------------------------ helpers
     def _stream_ptr(self, stream) -> ctypes.c_void_p:
@@ -388,7 +389,40 @@ class DeviceEngine:
             data = np.ascontiguousarray(data)
         return data, code
 
-    def filter_device(self, d_x, taps: np.ndarray, d_out=None, stream=None, strategy=None):
+    # A job of at least this many channel-samples gets the kernel specialised for its plan
+    # (built once per plan, ~1 s); smaller one-off jobs keep the pre-built kernels.
+    SPECIALISE_FROM = 1 << 24
+
+    def _filter_options(self, job_samples: int, kernel=None, tuning=None):
+        opts = _native.FilterOptions()
+        if kernel is None:
+            kernel = int(os.environ.get("PYPARRM_B200_FILTER_KERNEL", _native.KERNEL_AUTO))
+            if kernel == _native.KERNEL_AUTO and job_samples >= self.SPECIALISE_FROM:
+                kernel = -1  # specialise when the plan allows, else whatever AUTO picks
+        opts.kernel = _native.KERNEL_AUTO if kernel == -1 else int(kernel)
+        opts.try_special = kernel == -1
+        for name, value in (tuning or {}).items():
+            setattr(opts, name, int(value))
+        return opts
+
+    def _apply(self, opts, *args):
+        """parrm_filter_apply_ex; a job marked for specialisation tries that kernel first."""
+        if opts.try_special:
+            opts.kernel = _native.KERNEL_SPECIALISED
+            status = lib.parrm_filter_apply_ex(*args[:-1], ctypes.byref(opts), args[-1])
+            if status == 0:
+                self.last_filter_kernel = _native.filter_last_kernel()
+                return
+            if status != 4:  # anything but "cannot specialise this plan / no NVRTC here"
+                check(status, "parrm_filter_apply_ex")
+            opts.kernel = _native.KERNEL_AUTO
+            opts.try_special = False
+        check(lib.parrm_filter_apply_ex(*args[:-1], ctypes.byref(opts), args[-1]),
+              "parrm_filter_apply_ex")
+        self.last_filter_kernel = _native.filter_last_kernel()
+
+    def filter_device(self, d_x, taps: np.ndarray, d_out=None, stream=None, strategy=None,
+                      kernel=None, tuning=None):
         """Filter a device-resident [C, T] tensor (float64 or float32); returns a device tensor."""
         t = self.torch
         code = {t.float64: _native.F64, t.float32: _native.F32}[d_x.dtype]
@@ -399,13 +433,13 @@ class DeviceEngine:
         if d_out is None:
             d_out = t.empty((n_chans, n_samples), dtype=d_x.dtype, device=d_x.device)
         stream = stream or t.cuda.current_stream()
+        opts = self._filter_options(n_chans * n_samples, kernel, tuning)
         for c0 in range(0, n_chans, 65535):
             c1 = min(c0 + 65535, n_chans)
-            check(lib.parrm_filter_apply(
-                _vp(d_x[c0:c1].data_ptr()), d_x.stride(0), 0, n_samples,
+            self._apply(
+                opts, _vp(d_x[c0:c1].data_ptr()), d_x.stride(0), 0, n_samples,
                 _vp(d_out[c0:c1].data_ptr()), d_out.stride(0), 0, n_samples, n_samples, c1 - c0,
-                _vp(d_plan.data_ptr()), _vp(h_plan.ctypes.data), code, self._stream_ptr(stream)),
-                "parrm_filter_apply")
+                _vp(d_plan.data_ptr()), _vp(h_plan.ctypes.data), code, self._stream_ptr(stream))
             self.launches += 1
         return d_out
 
@@ -421,10 +455,11 @@ class DeviceEngine:
             h_plan, d_plan, _ = self._plan(taps, _native.F64)
             d_x = t.from_numpy(chunk).to(self.device)
             d_out = t.empty((n_chans, t1 - t0), dtype=t.float64, device=self.device)
-            check(lib.parrm_filter_apply(
-                _vp(d_x.data_ptr()), n_x, x0, n_x, _vp(d_out.data_ptr()), t1 - t0, t0, t1 - t0,
-                n_total, n_chans, _vp(d_plan.data_ptr()), _vp(h_plan.ctypes.data), _native.F64,
-                self._stream_ptr(t.cuda.current_stream())), "parrm_filter_apply")
+            opts = self._filter_options(n_chans * (t1 - t0))
+            self._apply(
+                opts, _vp(d_x.data_ptr()), n_x, x0, n_x, _vp(d_out.data_ptr()), t1 - t0, t0,
+                t1 - t0, n_total, n_chans, _vp(d_plan.data_ptr()), _vp(h_plan.ctypes.data),
+                _native.F64, self._stream_ptr(t.cuda.current_stream()))
             self.launches += 1
             return d_out.cpu().numpy()
 
@@ -445,6 +480,7 @@ class DeviceEngine:
         code = _native.F32 if compute_f32 else _native.F64
         with self._lock, t.cuda.device(self.device):
             h_plan, d_plan, (w_lo, w_hi) = self._plan(taps, code, strategy)
+            opts = self._filter_options(n_chans * n_samples)
             span = w_hi - w_lo
             row_bytes = n_samples * 8
             # chunk list: (c0, c1, t0, t1, x0, x1) -- channels [c0,c1), outputs [t0,t1), inputs [x0,x1)
@@ -507,10 +543,9 @@ class DeviceEngine:
                                                        n_c * n_x, s_run), "parrm_convert_f64_to_f32")
                     self.launches += 1
                     d_in_ptr, d_out_ptr = x32.data_ptr(), y32.data_ptr()
-                check(lib.parrm_filter_apply(
-                    _vp(d_in_ptr), n_x, x0, n_x, _vp(d_out_ptr), n_o, t0, n_o, n_samples, n_c,
-                    _vp(d_plan.data_ptr()), _vp(h_plan.ctypes.data), code, s_run),
-                    "parrm_filter_apply")
+                self._apply(
+                    opts, _vp(d_in_ptr), n_x, x0, n_x, _vp(d_out_ptr), n_o, t0, n_o, n_samples,
+                    n_c, _vp(d_plan.data_ptr()), _vp(h_plan.ctypes.data), code, s_run)
                 self.launches += 1
                 if compute_f32:
                     check(lib.parrm_convert_f32_to_f64(_vp(tf32[k][1].data_ptr()),

@@ -19,8 +19,22 @@ F64, F32 = 0, 1
 DIR_BOTH, DIR_PAST, DIR_FUTURE = 0, 1, 2
 DIRECTIONS = {"both": DIR_BOTH, "past": DIR_PAST, "future": DIR_FUTURE}
 MAX_BANDWIDTH = 23
-ABI_VERSION = 3
+ABI_VERSION = 4
 PLAN_AUTO, PLAN_GATHER, PLAN_COMB = 0, 1, 2
+KERNEL_AUTO, KERNEL_GATHER, KERNEL_STRIP, KERNEL_SPECIALISED = 0, 1, 2, 3
+
+
+class FilterOptions(ctypes.Structure):
+    """``parrm_filter_options_t`` (include/parrm_b200.h); all zero = library defaults."""
+
+    _fields_ = [
+        ("kernel", c_int32),
+        ("steps_per_chunk", c_int32),
+        ("prefetch_chunks", c_int32),
+        ("ctas_per_sm", c_int32),
+        ("reserved", c_int32 * 4),
+    ]
+
 
 # name -> (restype, argtypes); mirrors include/parrm_b200.h one to one
 SIGNATURES = {
@@ -64,6 +78,15 @@ SIGNATURES = {
         [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
          c_int64, c_void_p, c_void_p, c_int, c_void_p],
     ),
+    "parrm_filter_apply_ex": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
+         c_int64, c_void_p, c_void_p, c_int, POINTER(FilterOptions), c_void_p],
+    ),
+    "parrm_filter_last_kernel": (c_char_p, []),
+    "parrm_filter_specialise_check": (
+        c_int, [c_void_p, c_int, POINTER(FilterOptions), c_void_p, POINTER(c_size_t)]
+    ),
     "parrm_convert_f64_to_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "parrm_convert_f32_to_f64": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "parrm_fp64_fma_burn": (c_int, [c_int64, c_void_p, POINTER(c_double), c_void_p]),
@@ -101,6 +124,12 @@ def check(status: int, what: str) -> None:
     """Raise if a C-ABI call did not return PARRM_OK."""
     if status != 0:
         raise RuntimeError(f"{what} failed (status {status}): {last_error()}")
+
+
+def filter_last_kernel() -> str:
+    """Name of the kernel this thread's last ``parrm_filter_apply*`` call enqueued."""
+    name = lib.parrm_filter_last_kernel()
+    return name.decode() if name else ""
 
 
 def device_count() -> int:

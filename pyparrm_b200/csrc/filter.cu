@@ -12,9 +12,13 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "filter_jit.h"
 #include "filter_plan.h"
 
 namespace parrm {
+
+// name of the kernel the last parrm_filter_apply* call of this thread enqueued
+static thread_local const char* g_last_kernel = "";
 
 template <typename T>
 struct FilterArgs {
@@ -163,6 +167,7 @@ int launch_filter(const FilterArgs<T>& args_in, int64_t n_chans, cudaStream_t st
     dim3 grid((unsigned)blocks, (unsigned)n_chans);
     filter_gather_global_kernel<T><<<grid, kFilterThreads, 0, stream>>>(a);
     PARRM_LAUNCH_OK("filter_gather_global_kernel");
+    g_last_kernel = "filter_gather_global_kernel";
     return PARRM_OK;
   }
   // tile: at least the halo span (<= 2x read amplification from L2), in 1024-output passes
@@ -177,6 +182,7 @@ int launch_filter(const FilterArgs<T>& args_in, int64_t n_chans, cudaStream_t st
   dim3 grid((unsigned)ceil_div(a.n_out, tile), (unsigned)n_chans);
   filter_gather_smem_kernel<T><<<grid, kFilterThreads, smem, stream>>>(a);
   PARRM_LAUNCH_OK("filter_gather_smem_kernel");
+  g_last_kernel = "filter_gather_smem_kernel";
   return PARRM_OK;
 }
 
@@ -1255,6 +1261,7 @@ int launch_strip(const FilterPlanHeader* hdr, const int32_t* h_terms, const int3
                                      cudaSharedmemCarveoutMaxShared));
   kernel<<<unsigned(grid), block, pick_smem, stream>>>(a);
   PARRM_LAUNCH_OK("filter_comb_strip_kernel");
+  g_last_kernel = pick.pipe == 1 ? "filter_comb_pipe_kernel" : "filter_comb_strip_kernel";
   *launched = true;
   return PARRM_OK;
 }
@@ -1274,19 +1281,58 @@ int parrm_debug_strip_timing(unsigned long long* h_out, int reset) {
 }
 #endif
 
+const char* parrm_filter_last_kernel(void) { return parrm::g_last_kernel; }
+
+int parrm_filter_specialise_check(const void* h_plan, int dtype,
+                                  const parrm_filter_options_t* options, int32_t* shape,
+                                  size_t* cubin_bytes) {
+  using namespace parrm;
+  PARRM_REQUIRE(h_plan != nullptr, "parrm_filter_specialise_check: null plan");
+  const FilterPlanHeader* hdr = static_cast<const FilterPlanHeader*>(h_plan);
+  PARRM_REQUIRE(hdr->magic == kPlanMagic && hdr->version == kPlanVersion,
+                "parrm_filter_specialise_check: not a filter plan");
+  const int32_t* h_terms = reinterpret_cast<const int32_t*>(
+      static_cast<const unsigned char*>(h_plan) + hdr->terms_offset);
+  FilterTuning tune{0, options ? options->steps_per_chunk : 0,
+                    options ? options->prefetch_chunks : 0, options ? options->ctas_per_sm : 0};
+  CombEShape s;
+  if (!comb_e_shape(hdr, h_terms, dtype, &tune, &s)) {
+    set_error("parrm_filter_specialise_check: this plan is outside the specialised kernel's range");
+    return PARRM_ERR_UNSUPPORTED;
+  }
+  if (shape) {
+    const int32_t v[12] = {s.d, s.nk, s.m[0], s.m[1], s.nb[0], s.nb[1], s.n_plus + s.n_minus,
+                           s.u, s.pf, s.ctas, s.smem_bytes, ((s.d + 31) / 32) * 32 + 32};
+    for (int i = 0; i < 12; ++i) shape[i] = v[i];
+  }
+  return comb_e_compile_only(s, cubin_bytes);
+}
+
 int parrm_filter_apply(const void* d_x, int64_t ld_x, int64_t x_t0, int64_t n_x, void* d_out,
                        int64_t ld_out, int64_t t0, int64_t n_out, int64_t n_samples_total,
                        int64_t n_chans, const void* d_plan, const void* h_plan, int dtype,
                        void* stream) {
+  return parrm_filter_apply_ex(d_x, ld_x, x_t0, n_x, d_out, ld_out, t0, n_out, n_samples_total,
+                               n_chans, d_plan, h_plan, dtype, nullptr, stream);
+}
+
+int parrm_filter_apply_ex(const void* d_x, int64_t ld_x, int64_t x_t0, int64_t n_x, void* d_out,
+                          int64_t ld_out, int64_t t0, int64_t n_out, int64_t n_samples_total,
+                          int64_t n_chans, const void* d_plan, const void* h_plan, int dtype,
+                          const parrm_filter_options_t* options, void* stream) {
   using namespace parrm;
   PARRM_REQUIRE(d_plan != nullptr && h_plan != nullptr, "parrm_filter_apply: null plan");
   const FilterPlanHeader* hdr = static_cast<const FilterPlanHeader*>(h_plan);
   PARRM_REQUIRE(hdr->magic == kPlanMagic && hdr->version == kPlanVersion,
                 "parrm_filter_apply: not a filter plan");
   PARRM_REQUIRE(hdr->dtype == dtype, "parrm_filter_apply: plan built for another dtype");
+  PARRM_REQUIRE(dtype == PARRM_F64 || dtype == PARRM_F32, "parrm_filter_apply: bad dtype %d", dtype);
   PARRM_REQUIRE(n_chans >= 0 && n_out >= 0 && n_x >= 0 && n_samples_total >= 0,
                 "parrm_filter_apply: negative size");
   PARRM_REQUIRE(n_chans <= 65535, "parrm_filter_apply: more than 65535 channels per call");
+  const int want = options ? options->kernel : PARRM_FILTER_KERNEL_AUTO;
+  PARRM_REQUIRE(want >= PARRM_FILTER_KERNEL_AUTO && want <= PARRM_FILTER_KERNEL_SPECIALISED,
+                "parrm_filter_apply: unknown kernel choice %d", want);
   if (n_chans == 0 || n_out == 0) return PARRM_OK;
   PARRM_REQUIRE(d_x != nullptr && d_out != nullptr, "parrm_filter_apply: null data pointer");
   PARRM_REQUIRE(t0 >= 0 && t0 + n_out <= n_samples_total,
@@ -1306,30 +1352,56 @@ int parrm_filter_apply(const void* d_x, int64_t ld_x, int64_t x_t0, int64_t n_x,
       static_cast<const unsigned char*>(d_plan) + hdr->taps_offset);
   const int32_t* h_terms = reinterpret_cast<const int32_t*>(h_base + hdr->terms_offset);
   cudaStream_t s = as_stream(stream);
+
+  // 1. kernel specialised for this plan at run time (pattern-first comb, filter_comb_e.cuh).
+  //    Building it costs about a second once per plan, so short one-off calls keep the
+  //    pre-built kernels unless the specialisation already exists.
+  if (hdr->kind == kPlanComb &&
+      (want == PARRM_FILTER_KERNEL_AUTO || want == PARRM_FILTER_KERNEL_SPECIALISED)) {
+    FilterTuning tune{want, options ? options->steps_per_chunk : 0,
+                      options ? options->prefetch_chunks : 0, options ? options->ctas_per_sm : 0};
+    CombEShape shape;
+    const bool fits = comb_e_shape(hdr, h_terms, dtype, &tune, &shape);
+    const bool worth = want == PARRM_FILTER_KERNEL_SPECIALISED ||
+                       n_chans * n_out >= (int64_t(1) << 24) || (fits && comb_e_cached(shape));
+    if (fits && worth) {
+      const int rc = launch_comb_e(shape, d_x, d_out, d_taps, ld_x, x_t0, n_x, ld_out, t0, n_out,
+                                   n_samples_total, n_chans, s, nullptr);
+      if (rc == PARRM_OK) {
+        g_last_kernel = "parrm_filter_comb_e";
+        return rc;
+      }
+      if (rc != PARRM_ERR_UNSUPPORTED || want == PARRM_FILTER_KERNEL_SPECIALISED) return rc;
+    } else if (want == PARRM_FILTER_KERNEL_SPECIALISED) {
+      set_error("parrm_filter_apply: this plan is outside the specialised kernel's range");
+      return PARRM_ERR_UNSUPPORTED;
+    }
+  } else if (want == PARRM_FILTER_KERNEL_SPECIALISED) {
+    set_error("parrm_filter_apply: the specialised kernel needs a comb plan");
+    return PARRM_ERR_UNSUPPORTED;
+  }
+
+  const bool try_strip = hdr->kind == kPlanComb && want != PARRM_FILTER_KERNEL_GATHER;
   if (dtype == PARRM_F64) {
     FilterArgs<double> a{static_cast<const double*>(d_x), static_cast<double*>(d_out),
                          d_taps, ld_x, x_t0, n_x, ld_out, t0, n_out, n_samples_total,
                          hdr->n_taps, w_lo, w_hi, 0};
-    if (hdr->kind == kPlanComb) {
+    if (try_strip) {
       bool launched = false;
       const int rc = launch_strip<double>(hdr, h_terms, d_taps, a, n_chans, s, &launched);
       if (rc != PARRM_OK || launched) return rc;
     }
     return launch_filter<double>(a, n_chans, s);
   }
-  if (dtype == PARRM_F32) {
-    FilterArgs<float> a{static_cast<const float*>(d_x), static_cast<float*>(d_out),
-                        d_taps, ld_x, x_t0, n_x, ld_out, t0, n_out, n_samples_total,
-                        hdr->n_taps, w_lo, w_hi, 0};
-    if (hdr->kind == kPlanComb) {
-      bool launched = false;
-      const int rc = launch_strip<float>(hdr, h_terms, d_taps, a, n_chans, s, &launched);
-      if (rc != PARRM_OK || launched) return rc;
-    }
-    return launch_filter<float>(a, n_chans, s);
+  FilterArgs<float> a{static_cast<const float*>(d_x), static_cast<float*>(d_out),
+                      d_taps, ld_x, x_t0, n_x, ld_out, t0, n_out, n_samples_total,
+                      hdr->n_taps, w_lo, w_hi, 0};
+  if (try_strip) {
+    bool launched = false;
+    const int rc = launch_strip<float>(hdr, h_terms, d_taps, a, n_chans, s, &launched);
+    if (rc != PARRM_OK || launched) return rc;
   }
-  set_error("parrm_filter_apply: bad dtype %d", dtype);
-  return PARRM_ERR_INVALID_ARGUMENT;
+  return launch_filter<float>(a, n_chans, s);
 }
 
 }  // extern "C"

@@ -1,0 +1,464 @@
+// Comb filter, "pattern first" form: body of PARRM.filter_data (parrm.py:861-869) for tap
+// sets with comb structure (filter_plan.h), specialised at run time for one plan.
+//
+// This file is compiled twice: by nvcc with the defaults below (the cfg2 plan; build check,
+// SASS inspection) and by NVRTC from filter_jit.cu with every PE_* macro set from the plan, so
+// that the stride, the box lengths and every tap offset are immediates.
+//
+// The plan writes the tap sum as comb boxes over one stride d,
+//     sum_{w in taps} x[t-w] = sum_k sum_b sum_{q<M_k} x[t - a_kb - q d]  +/- single taps + c x[t].
+// Summing over the boxes first gives a short pattern  E_k[i] = sum_b x[i - a_kb]  (NB_k loads)
+// and the comb becomes a running sum of E_k along the chain t, t+d, t+2d, ...:
+//     S_k[t] = sum_{q<M_k} E_k[t - q d],     S_k[t + d] = S_k[t] + E_k[t + d] - E_k[t + d - M_k d].
+// One thread owns one chain (one residue of t mod d).  It keeps the last M_k values of E_k in
+// REGISTERS (statically indexed: the step loop is unrolled M_0 deep), so per output the shared
+// memory pipe sees only the NB_0 + NB_1 pattern loads, the single taps and x[t] -- for the
+// cfg2 filter (160 taps) 12 loads instead of 160, and no intermediate array at all.  The sums
+// are re-added from the register ring every M_0 steps, which bounds rounding drift.
+//
+// Data movement: a persistent CTA walks a strip of consecutive chunks (U*d samples) of one
+// channel.  A producer warp streams chunks HBM -> shared ring with TMA bulk copies
+// (cp.async.bulk + mbarrier complete_tx; every sample is read from HBM once per strip); the
+// first MIR ring chunks are mirrored behind the ring so the window a step reads is contiguous
+// and every load is  [chain pointer + immediate].  D/32 consumer warps wait on the `full`
+// barrier of the newest chunk, run U steps, and release the oldest chunk (`empty`).  Outputs
+// go straight from registers to HBM, 32 consecutive samples per warp store.
+//
+// Non-finite samples: an output whose tap window (or own sample) holds a NaN/Inf is 0, as the
+// reference's isfinite -> 0 replacement (parrm.py:869) intends; the bad pattern value is
+// dropped from the ring, so outputs past the window are exact again.
+#pragma once
+
+#ifdef __CUDACC_RTC__
+typedef signed char int8_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t;
+#else
+#include <stdint.h>
+#endif
+
+#ifndef PE_D  // defaults: BASELINE cfg2 (period 2000/130 samples, half width 2000, both directions)
+#define PE_T double
+#define PE_D 200
+#define PE_NK 2
+#define PE_M0 20
+#define PE_M1 10
+#define PE_NB0 7
+#define PE_NB1 4
+#define PE_OFF0 -1969, -1954, -1923, -1877, -1846, -1831, -1800
+#define PE_OFF1 -2000, -1908, 108, 200
+#define PE_NPLUS 0
+#define PE_PLUS 0
+#define PE_NMINUS 0
+#define PE_MINUS 0
+#define PE_CENTRE 0
+#define PE_U 4
+#define PE_PF 4
+#define PE_NTAPS 160
+#define PE_WLO -2000
+#define PE_WHI 2000
+#define PE_BACK 200
+#define PE_FWD 2000
+#define PE_CTAS 2
+#endif
+#ifndef PE_TMAX  // largest finite value of PE_T
+#define PE_TMAX 1.7976931348623157e308
+#endif
+
+namespace parrm_e {
+
+typedef PE_T T;
+constexpr int D = PE_D;            // comb stride = chains per strip
+constexpr int NK = PE_NK;          // box lengths in use (1 or 2), M0 >= M1
+constexpr int M0 = PE_M0;
+constexpr int M1 = PE_M1;
+constexpr int NB0 = PE_NB0;
+constexpr int NB1 = PE_NB1;
+constexpr int NPLUS = PE_NPLUS;
+constexpr int NMINUS = PE_NMINUS;
+constexpr int CENTRE = PE_CENTRE;  // coefficient of x[t] inside the tap sum (<= 0)
+constexpr int U = PE_U;            // steps per chunk
+constexpr int PF = PE_PF;          // chunks in flight beyond the window
+constexpr int NTAPS = PE_NTAPS;
+constexpr int WLO = PE_WLO;        // min(w_min, 0)
+constexpr int WHI = PE_WHI;        // max(w_max, 0)
+constexpr int BACK = PE_BACK;      // largest offset any load reaches back from t (>= 0)
+constexpr int FWD = PE_FWD;        // ... forward (>= 0)
+constexpr int ES = int(sizeof(T));
+constexpr int VEC = 16 / ES;
+constexpr int CH = U * D;                        // samples per chunk
+constexpr int HB = (BACK + CH - 1) / CH;         // chunks behind the current one a step reads
+constexpr int HF = (FWD + CH - 1) / CH;          // chunks ahead
+constexpr int MIR = HB + HF;                     // mirrored ring chunks
+constexpr int Q = HB + HF + 1 + PF;              // ring chunks
+constexpr int NPG = (M0 + U - 1) / U;            // priming groups (fill the register rings)
+constexpr int NW = (D + 31) / 32;                // consumer warps
+constexpr int NT = NW * 32 + 32;                 // + one producer warp
+constexpr int BAR_BYTES = ((2 * Q * 8 + 127) / 128) * 128;
+constexpr int SMEM_BYTES = BAR_BYTES + (Q + MIR) * CH * ES;
+constexpr bool STATIC_GROUPS = (M0 % U) == 0;  // chunk boundaries at fixed steps of the block
+static_assert((CH * ES) % 16 == 0, "chunk must be a whole number of 16-byte units");
+static_assert(M0 >= M1 && M0 >= 1, "box lengths ordered");
+
+// tap offsets of the plan (compile-time tables; every use folds to an immediate)
+__host__ __device__ constexpr int off0(int b) {
+  constexpr int t[NB0 > 0 ? NB0 : 1] = {PE_OFF0};
+  return t[b];
+}
+__host__ __device__ constexpr int off1(int b) {
+  constexpr int t[NB1 > 0 ? NB1 : 1] = {PE_OFF1};
+  return t[b];
+}
+__host__ __device__ constexpr int plus_tap(int i) {
+  constexpr int t[NPLUS > 0 ? NPLUS : 1] = {PE_PLUS};
+  return t[i];
+}
+__host__ __device__ constexpr int minus_tap(int i) {
+  constexpr int t[NMINUS > 0 ? NMINUS : 1] = {PE_MINUS};
+  return t[i];
+}
+
+struct Args {
+  const T* x;
+  T* out;
+  const int32_t* taps;  // device, ascending (edge counts only)
+  int64_t ld_x, x_t0, n_x;
+  int64_t ld_out, t0, n_out;
+  int64_t n_total;
+  int64_t total_groups;  // n_chans * groups_per_chan
+  int32_t groups_per_chan;
+  int32_t pad;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ int64_t floor_div(int64_t a, int64_t b) {
+  int64_t q = a / b;
+  return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+__device__ __forceinline__ int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
+__device__ __forceinline__ int64_t max64(int64_t a, int64_t b) { return a > b ? a : b; }
+__device__ __forceinline__ bool finite_val(T v) { return fabs(v) <= T(PE_TMAX); }
+
+// Recording edges (outputs whose tap window leaves [0, n_total), and chunks only partly inside
+// the requested output range): mean over the in-range taps, parrm.py:861-866.  Out of line --
+// a few chunks per channel take this path and it must not bloat the unrolled step loop.
+__device__ __noinline__ void edge_store(const int32_t* __restrict__ taps, T* __restrict__ orow,
+                                        int64_t t, int64_t t0, int64_t n_out, int64_t n_total,
+                                        T xc, T tot, bool zero) {
+  if (t < t0 || t >= t0 + n_out) return;
+  auto upper = [&](int64_t v) {  // #taps <= v
+    int lo = 0, hi = NTAPS;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (int64_t(taps[mid]) <= v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  };
+  const int n_in = upper(t) - upper(t - n_total);  // taps w with 0 <= t - w < n_total
+  T y = T(0);
+  if (!zero && n_in > 0) {
+    y = xc - tot / T(n_in);
+    if (!(fabs(y) <= T(PE_TMAX))) y = T(0);
+  }
+  orow[t] = y;
+}
+
+// Per-piece walking state of a consumer thread that changes at chunk boundaries.
+struct Walk {
+  int pb;          // byte offset (from smem_raw) of the sample HB*CH before the current output
+  int rslot;       // oldest live ring slot (next to release)
+  int fslot;       // next ring slot to wait for
+  uint32_t fphase; // parity of that fill
+  int g;           // group (chunk of outputs) inside the piece; -1 before the first
+  int mode;        // 0 priming (no outputs), 1 interior, 2 recording edge / partial range
+  int more;        // 0 once the piece is finished
+  int64_t t_out;   // global time of the thread's output at the first step of the group
+};
+
+// Ends group g (releases its oldest chunk) and opens group g + 1 (waits for its newest chunk).
+__device__ __noinline__ Walk next_group(Walk w, uint32_t bars, int lane, int c, int n_groups,
+                                        int64_t T0, int64_t t0, int64_t n_out, int64_t n_total) {
+  if (w.g >= 0) {
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + (Q + w.rslot) * 8)
+                   : "memory");
+    }
+    w.pb += CH * ES;
+    if (++w.rslot == Q) {
+      w.rslot = 0;
+      w.pb -= Q * CH * ES;
+    }
+  }
+  ++w.g;
+  if (w.g == n_groups) {
+    w.more = 0;
+    return w;
+  }
+  mbar_wait(bars + w.fslot * 8, w.fphase);
+  if (++w.fslot == Q) {
+    w.fslot = 0;
+    w.fphase ^= 1u;
+  }
+  const int64_t Tn = T0 + int64_t(w.g) * CH;  // T0: global time of the piece's first group
+  w.t_out = Tn + c;
+  if (w.g < NPG) {
+    w.mode = 0;
+  } else {
+    const bool interior = (Tn - WHI >= 0) && (Tn + CH - WLO <= n_total);
+    const bool all_out = (Tn >= t0) && (Tn + CH <= t0 + n_out);
+    w.mode = (interior && all_out) ? 1 : 2;
+  }
+  return w;
+}
+
+extern "C" __global__ void __launch_bounds__(NT, PE_CTAS) parrm_filter_comb_e(const Args a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw);  // [Q] chunk landed
+  uint64_t* const empty = full + Q;                              // [Q] chunk released
+  T* const ring = reinterpret_cast<T*>(smem_raw + BAR_BYTES);    // (Q + MIR) chunks
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const bool is_producer = tid >= NW * 32;
+
+  if (tid == 0) {
+    for (int s = 0; s < Q; ++s) {
+      mbar_init(&full[s], 1);    // the producer's elected lane arrives (plus the TMA bytes)
+      mbar_init(&empty[s], NW);  // one lane of every consumer warp arrives
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int64_t lo_valid = max64(0, a.x_t0);
+  const int64_t hi_valid = min64(a.n_total, a.x_t0 + a.n_x);
+  const int gpc = a.groups_per_chan;
+  const int64_t G_begin = a.total_groups * int64_t(blockIdx.x) / int64_t(gridDim.x);
+  const int64_t G_end = a.total_groups * int64_t(blockIdx.x + 1) / int64_t(gridDim.x);
+  const uint32_t bars = smem_u32(smem_raw);
+
+  // Chunks are numbered by one counter that runs on through all pieces of this CTA: chunk
+  // number s lives in ring slot s % Q and is the (s / Q)-th fill of that slot.  Both roles
+  // keep (slot, phase) of their own position in that sequence.
+  int fslot = 0;        // producer: next slot to fill;  consumer: next slot to wait for
+  uint32_t fphase = 0;  // parity of that fill
+  int rslot = 0;        // consumer: oldest live slot (next to release)
+
+  for (int64_t G = G_begin; G < G_end;) {
+    const int64_t chan = G / gpc;
+    const int s0 = int(G - chan * gpc);
+    const int s1 = int(min64(gpc, s0 + (G_end - G)));
+    G += s1 - s0;
+    const T* const xrow = a.x + chan * a.ld_x - a.x_t0;  // xrow[g] = sample at global time g
+    T* const orow = a.out + chan * a.ld_out - a.t0;      // orow[g]
+    const int gamma = int((VEC - int((reinterpret_cast<uintptr_t>(xrow) / ES) % VEC)) % VEC);
+    const int64_t j_first = floor_div(a.t0 - gamma, CH);
+    const int64_t j_last = floor_div(a.t0 + a.n_out - 1 - gamma, CH);
+    const int64_t n_first = j_first + s0;                      // first group with outputs
+    const int64_t n_end = min64(j_first + s1, j_last + 1);
+    if (n_first >= n_end) continue;
+    const int n_groups = NPG + int(n_end - n_first);           // priming groups first
+    const int n_chunks = n_groups + HB + HF;
+    const int64_t c_first = n_first - NPG - HB;                // first chunk the piece reads
+
+    if (is_producer) {
+      // ------------------------------ producer warp ------------------------------
+      for (int i = 0; i < n_chunks; ++i) {
+        const int64_t g0 = gamma + (c_first + i) * int64_t(CH);
+        T* const dst = ring + fslot * CH;
+        mbar_wait(bars + (Q + fslot) * 8, fphase ^ 1u);  // the previous fill has been released
+        if (g0 >= lo_valid && g0 + CH <= hi_valid) {
+          if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const bool mirror = fslot < MIR;
+            mbar_expect_tx(&full[fslot], uint32_t(CH * ES) * (mirror ? 2u : 1u));
+            bulk_g2s(dst, xrow + g0, uint32_t(CH * ES), &full[fslot]);
+            if (mirror) bulk_g2s(dst + Q * CH, xrow + g0, uint32_t(CH * ES), &full[fslot]);
+          }
+        } else {  // chunk crosses an end of the available samples: zero fill
+          for (int e = lane; e < CH; e += 32) {
+            const int64_t g = g0 + e;
+            const T v = (g >= lo_valid && g < hi_valid) ? xrow[g] : T(0);
+            dst[e] = v;
+            if (fslot < MIR) dst[Q * CH + e] = v;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[fslot]);
+        }
+        if (++fslot == Q) {
+          fslot = 0;
+          fphase ^= 1u;
+        }
+      }
+      continue;
+    }
+
+    // ------------------------------ consumer warps ------------------------------
+    const int c = tid < D ? tid : D - 1;  // lanes past the last chain shadow it (no stores)
+    const bool lane_stores = tid < D;
+    for (int i = 0; i < HB + HF; ++i) {   // the window of the first group, except its newest chunk
+      mbar_wait(bars + fslot * 8, fphase);
+      if (++fslot == Q) {
+        fslot = 0;
+        fphase ^= 1u;
+      }
+    }
+    T r0[M0];
+    T r1[NK > 1 ? M0 : 1];
+#pragma unroll
+    for (int s = 0; s < M0; ++s) r0[s] = T(0);
+#pragma unroll
+    for (int s = 0; s < (NK > 1 ? M0 : 1); ++s) r1[s] = T(0);
+    const T inv_n = T(1) / T(NTAPS);
+    const int64_t T0 = gamma + (n_first - NPG) * int64_t(CH);
+    Walk w;
+    w.pb = BAR_BYTES + (rslot * CH + c) * ES;
+    w.rslot = rslot;
+    w.fslot = fslot;
+    w.fphase = fphase;
+    w.g = -1;
+    w.mode = 0;
+    w.more = 1;
+    w.t_out = 0;
+    w = next_group(w, bars, lane, c, n_groups, T0, a.t0, a.n_out, a.n_total);
+    int k = 0;       // steps done in this piece
+    int k_dead = 0;  // outputs of steps < k_dead have a non-finite sample in their window
+    int j = 0;       // step inside the group (dynamic grouping only)
+
+    while (w.more) {
+      // fresh sums from the rings (bounds the drift of the running update)
+      T S0 = r0[0], S1 = T(0);
+#pragma unroll
+      for (int s = 1; s < M0; ++s) S0 += r0[s];
+      if (NK > 1) {
+        S1 = r1[M0 - M1];
+#pragma unroll
+        for (int s = M0 - M1 + 1; s < M0; ++s) S1 += r1[s];
+      }
+#pragma unroll
+      for (int s = 0; s < M0; ++s) {
+        // with U | M0 the position inside the group is static and folds into the immediates
+        const int js = STATIC_GROUPS ? (s % U) : 0;
+        const unsigned char* const p = smem_raw + w.pb;
+        auto ld = [&](int off) {  // sample at (current output time - off)
+          return *reinterpret_cast<const T*>(p + (HB * CH + js * D - off) * ES);
+        };
+        T e0 = ld(off0(0));  // two partial sums: shorter dependent chains
+        if (NB0 > 1) {
+          T e0b = ld(off0(1));
+#pragma unroll
+          for (int b = 2; b < NB0; ++b) {
+            if (b & 1) e0b += ld(off0(b)); else e0 += ld(off0(b));
+          }
+          e0 += e0b;
+        }
+        if (!finite_val(e0)) {  // dropped from the sums; its window's outputs are 0
+          e0 = T(0);
+          k_dead = max(k_dead, k + M0);
+        }
+        S0 += e0 - r0[s];
+        r0[s] = e0;
+        T tot = S0;
+        if (NK > 1) {
+          T e1 = ld(off1(0));
+          if (NB1 > 1) {
+            T e1b = ld(off1(1));
+#pragma unroll
+            for (int b = 2; b < NB1; ++b) {
+              if (b & 1) e1b += ld(off1(b)); else e1 += ld(off1(b));
+            }
+            e1 += e1b;
+          }
+          if (!finite_val(e1)) {
+            e1 = T(0);
+            k_dead = max(k_dead, k + M1);
+          }
+          S1 += e1 - r1[(s + M0 - M1) % M0];
+          r1[s] = e1;
+          tot += S1;
+        }
+#pragma unroll
+        for (int i = 0; i < NPLUS; ++i) tot += ld(plus_tap(i));
+#pragma unroll
+        for (int i = 0; i < NMINUS; ++i) tot -= ld(minus_tap(i));
+        const T xc = ld(0);
+        if (CENTRE != 0) tot = fma(T(CENTRE), xc, tot);
+        T y = fma(-tot, inv_n, xc);
+        const bool zero = !finite_val(y) || (k < k_dead);
+        if (zero) y = T(0);
+        if (w.mode == 1) {
+          if (lane_stores) orow[w.t_out + js * D] = y;
+        } else if (w.mode == 2) {
+          if (lane_stores)
+            edge_store(a.taps, orow, w.t_out + js * D, a.t0, a.n_out, a.n_total, xc, tot, zero);
+        }
+        ++k;
+        bool boundary;
+        if (STATIC_GROUPS) {
+          boundary = (s % U) == U - 1;
+        } else {
+          w.pb += D * ES;
+          w.t_out += D;
+          boundary = ++j == U;
+        }
+        if (boundary) {
+          if (!STATIC_GROUPS) {
+            j = 0;
+            w.pb -= CH * ES;  // next_group advances by one chunk
+          }
+          w = next_group(w, bars, lane, c, n_groups, T0, a.t0, a.n_out, a.n_total);
+          if (!w.more) break;
+        }
+      }
+    }
+    rslot = w.rslot;
+    fslot = w.fslot;
+    fphase = w.fphase;
+    // release the rest of the window (chunks the last group still held)
+    __syncwarp();
+    for (int i = 0; i < HB + HF; ++i) {
+      if (lane == 0) mbar_arrive(&empty[rslot]);
+      if (++rslot == Q) rslot = 0;
+    }
+  }
+}
+
+}  // namespace parrm_e
