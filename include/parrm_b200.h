@@ -153,7 +153,7 @@ int parrm_build_taps(double period, double period_half_width, int64_t filter_hal
  * ~10x fewer shared-memory loads than one load per tap.  parrm_filter_plan_info() exposes the
  * decomposition (tests expand it back into the tap set).
  * ---------------------------------------------------------------------- */
-size_t parrm_filter_plan_bytes(int32_t n_taps);
+size_t parrm_filter_plan_bytes(const int32_t* h_taps, int32_t n_taps);
 int parrm_filter_plan(const int32_t* h_taps, int32_t n_taps, int dtype, int strategy,
                       void* h_plan, size_t plan_bytes);
 /* info[0..15] = kind, stride, n_kinds, window0, window1, n_box0, n_box1, n_plus, n_minus,

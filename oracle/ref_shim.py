@@ -1,9 +1,11 @@
-"""Import the UNMODIFIED reference from /root/reference -- build container only.
+"""Import the UNMODIFIED reference: from /root/reference in the build container, else from
+the verbatim copy ``oracle/_ref/pyparrm`` made by ``oracle/vendor_ref.py`` (git-ignored; it
+travels to the GPU box, where /root/reference does not exist).
 
-TEST INFRASTRUCTURE.  ``/root/reference`` does not exist on the GPU box, so
-nothing under ``tests/ -m gpu``, ``smoke()`` or ``bench.py`` may call this; it
-is used by ``oracle/make_golden.py`` (which records reference outputs into
-``tests/golden/``) and by CPU tests that skip when the path is absent.
+TEST / BENCH INFRASTRUCTURE.  Used by ``oracle/make_golden.py`` (records reference outputs
+into ``tests/golden/``), by CPU tests that skip when neither location exists, and by the CPU
+legs of ``bench.py`` (``--impl reference`` and ``cpu_baseline``), which time the reference's
+own methods.  Nothing in ``pyparrm_b200/`` imports this.
 
 The reference's ``import pyparrm`` fails here because ``pqdm`` and
 ``matplotlib`` are not installed (``parrm.py:9``, ``_utils/_plotting.py:10-11``)
@@ -25,11 +27,27 @@ import sys
 import types
 from concurrent.futures import ThreadPoolExecutor
 
-REFERENCE_SRC = "/root/reference/src"
+_MOUNTED = "/root/reference/src"
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _source_dir() -> str | None:
+    for base in (_MOUNTED, _VENDORED):
+        if os.path.isfile(os.path.join(base, "pyparrm", "parrm.py")):
+            return base
+    return None
+
+
+REFERENCE_SRC = _source_dir() or _MOUNTED
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_SRC, "pyparrm"))
+    return _source_dir() is not None
+
+
+def reference_location() -> str:
+    """Where the reference would be imported from ("" when it is nowhere)."""
+    return _source_dir() or ""
 
 
 def _thread_map(array, function, n_jobs, argument_type=None, **_ignored):
@@ -72,13 +90,15 @@ def _install_stand_ins() -> None:
 
 def import_reference():
     """Return the reference ``pyparrm`` package (raises if it is not mounted)."""
-    if not reference_available():
-        raise ImportError(f"reference not mounted at {REFERENCE_SRC}")
+    src = _source_dir()
+    if src is None:
+        raise ImportError(f"reference neither mounted at {_MOUNTED} nor vendored at {_VENDORED} "
+                          "(python oracle/vendor_ref.py)")
     _install_stand_ins()
-    if REFERENCE_SRC not in sys.path:
-        sys.path.insert(0, REFERENCE_SRC)
+    if src not in sys.path:
+        sys.path.insert(0, src)
     import pyparrm
 
-    if not os.path.abspath(pyparrm.__file__).startswith(REFERENCE_SRC):
+    if not os.path.abspath(pyparrm.__file__).startswith(src):
         raise ImportError(f"'pyparrm' resolved to {pyparrm.__file__}, not the reference")
     return pyparrm

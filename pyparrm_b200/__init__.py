@@ -8,19 +8,43 @@ or :func:`install_as_pyparrm` lets existing callers run unchanged.
 __version__ = "1.2.0dev+b200.r1"
 
 from .data import get_example_data_paths
-from .parrm import PARRM
-from ._engine import pinned_empty
-from ._sharding import disable as disable_sharding
-from ._sharding import enable as enable_sharding
+
+# Everything that needs libparrm_b200.so is resolved on first use (PEP 562), so helpers with no
+# device work -- ``pyparrm_b200.synthetic``, ``pyparrm_b200.data`` -- can be imported without
+# mapping the library (bench.py's reference arm relies on that).  Accessing ``PARRM`` on a
+# machine where the library is not built raises ImportError: there is no CPU fallback.
+_LAZY = {
+    "PARRM": (".parrm", "PARRM"),
+    "pinned_empty": ("._engine", "pinned_empty"),
+    "enable_sharding": ("._sharding", "enable"),
+    "disable_sharding": ("._sharding", "disable"),
+}
+
+
+def __getattr__(name):
+    if name in _LAZY:
+        import importlib
+
+        module, attr = _LAZY[name]
+        value = getattr(importlib.import_module(module, __name__), attr)
+        globals()[name] = value
+        return value
+    if name in ("parrm", "_engine", "_native", "_sharding", "_neldermead", "_utils"):
+        import importlib
+
+        return importlib.import_module("." + name, __name__)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
 
 
 def install_as_pyparrm() -> None:
     """Register this package under the name ``pyparrm`` so ``from pyparrm import PARRM`` works."""
     import sys
 
+    import importlib
+
     sys.modules.setdefault("pyparrm", sys.modules[__name__])
-    sys.modules.setdefault("pyparrm.data", sys.modules[__name__ + ".data"])
-    sys.modules.setdefault("pyparrm.parrm", sys.modules[__name__ + ".parrm"])
+    for sub in ("data", "parrm"):
+        sys.modules.setdefault("pyparrm." + sub, importlib.import_module("." + sub, __name__))
 
 
 __all__ = ["PARRM", "get_example_data_paths", "pinned_empty", "install_as_pyparrm",

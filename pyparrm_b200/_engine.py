@@ -363,7 +363,7 @@ class DeviceEngine:
         hit = self._plans.get(key)
         if hit is not None:
             return hit
-        nbytes = lib.parrm_filter_plan_bytes(int(taps.shape[0]))
+        nbytes = lib.parrm_filter_plan_bytes(_vp(taps.ctypes.data), int(taps.shape[0]))
         h_plan = np.zeros(nbytes, dtype=np.uint8)
         check(lib.parrm_filter_plan(_vp(taps.ctypes.data), int(taps.shape[0]), dtype_code,
                                     int(strategy), _vp(h_plan.ctypes.data), nbytes),

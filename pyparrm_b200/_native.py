@@ -70,7 +70,7 @@ SIGNATURES = {
     "parrm_build_taps": (
         c_int, [c_double, c_double, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]
     ),
-    "parrm_filter_plan_bytes": (c_size_t, [c_int32]),
+    "parrm_filter_plan_bytes": (c_size_t, [c_void_p, c_int32]),
     "parrm_filter_plan": (c_int, [c_void_p, c_int32, c_int, c_int, c_void_p, c_size_t]),
     "parrm_filter_plan_info": (c_int, [c_void_p, c_void_p, c_void_p, c_int32]),
     "parrm_filter_apply": (
@@ -147,7 +147,7 @@ def plan_filter(taps, dtype: int = F64, strategy: int = PLAN_AUTO):
     import numpy as np
 
     taps = np.ascontiguousarray(taps, dtype=np.int32)
-    nbytes = lib.parrm_filter_plan_bytes(int(taps.shape[0]))
+    nbytes = lib.parrm_filter_plan_bytes(taps.ctypes.data, int(taps.shape[0]))
     plan = np.zeros(nbytes, dtype=np.uint8)
     check(lib.parrm_filter_plan(taps.ctypes.data, int(taps.shape[0]), dtype, strategy,
                                 plan.ctypes.data, nbytes), "parrm_filter_plan")

@@ -1365,8 +1365,11 @@ int parrm_filter_apply_ex(const void* d_x, int64_t ld_x, int64_t x_t0, int64_t n
     const bool worth = want == PARRM_FILTER_KERNEL_SPECIALISED ||
                        n_chans * n_out >= (int64_t(1) << 24) || (fits && comb_e_cached(shape));
     if (fits && worth) {
-      const int rc = launch_comb_e(shape, d_x, d_out, d_taps, ld_x, x_t0, n_x, ld_out, t0, n_out,
-                                   n_samples_total, n_chans, s, nullptr);
+      const unsigned char* d_base = static_cast<const unsigned char*>(d_plan);
+      const int rc = launch_comb_e(
+          shape, d_x, d_out, reinterpret_cast<const int32_t*>(d_base + hdr->count_offset),
+          reinterpret_cast<const double*>(d_base + hdr->recip_offset), ld_x, x_t0, n_x, ld_out,
+          t0, n_out, n_samples_total, n_chans, s, nullptr);
       if (rc == PARRM_OK) {
         g_last_kernel = "parrm_filter_comb_e";
         return rc;

@@ -47,20 +47,20 @@ typedef unsigned long long uintptr_t;
 #define PE_M0 20
 #define PE_M1 10
 #define PE_NB0 7
-#define PE_NB1 4
+#define PE_NB1 2
 #define PE_OFF0 -1969, -1954, -1923, -1877, -1846, -1831, -1800
-#define PE_OFF1 -2000, -1908, 108, 200
-#define PE_NPLUS 0
-#define PE_PLUS 0
+#define PE_OFF1 -1908, 108
+#define PE_NPLUS 1
+#define PE_PLUS -2000
 #define PE_NMINUS 0
 #define PE_MINUS 0
-#define PE_CENTRE 0
-#define PE_U 4
+#define PE_CENTRE -1
+#define PE_U 5
 #define PE_PF 4
 #define PE_NTAPS 160
 #define PE_WLO -2000
 #define PE_WHI 2000
-#define PE_BACK 200
+#define PE_BACK 108
 #define PE_FWD 2000
 #define PE_CTAS 2
 #endif
@@ -71,6 +71,7 @@ typedef unsigned long long uintptr_t;
 namespace parrm_e {
 
 typedef PE_T T;
+typedef double T2;
 constexpr int D = PE_D;            // comb stride = chains per strip
 constexpr int NK = PE_NK;          // box lengths in use (1 or 2), M0 >= M1
 constexpr int M0 = PE_M0;
@@ -124,7 +125,8 @@ __host__ __device__ constexpr int minus_tap(int i) {
 struct Args {
   const T* x;
   T* out;
-  const int32_t* taps;  // device, ascending (edge counts only)
+  const int32_t* count;  // plan table: count[v - (WLO - 1)] = #{taps <= v}, WLO - 1 <= v <= WHI
+  const T2* recip;       // plan table: 0, 1/1, 1/2, ... 1/NTAPS (float64)
   int64_t ld_x, x_t0, n_x;
   int64_t ld_out, t0, n_out;
   int64_t n_total;
@@ -178,27 +180,19 @@ __device__ __forceinline__ int64_t max64(int64_t a, int64_t b) { return a > b ? 
 __device__ __forceinline__ bool finite_val(T v) { return fabs(v) <= T(PE_TMAX); }
 
 // Recording edges (outputs whose tap window leaves [0, n_total), and chunks only partly inside
-// the requested output range): mean over the in-range taps, parrm.py:861-866.  Out of line --
-// a few chunks per channel take this path and it must not bloat the unrolled step loop.
-__device__ __noinline__ void edge_store(const int32_t* __restrict__ taps, T* __restrict__ orow,
-                                        int64_t t, int64_t t0, int64_t n_out, int64_t n_total,
+// the requested output range): mean over the in-range taps, parrm.py:861-866.  The number of
+// in-range taps  #{w : 0 <= t - w < n_total} = #{w <= t} - #{w <= t - n_total}  comes from the
+// plan's cumulative table, its reciprocal from the plan's reciprocal table (no search, no
+// division: this sits in the unrolled step loop and must stay small).
+__device__ __forceinline__ T edge_value(const int32_t* __restrict__ count,
+                                        const T2* __restrict__ recip, int64_t t, int64_t n_total,
                                         T xc, T tot, bool zero) {
-  if (t < t0 || t >= t0 + n_out) return;
-  auto upper = [&](int64_t v) {  // #taps <= v
-    int lo = 0, hi = NTAPS;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (int64_t(taps[mid]) <= v) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-  };
-  const int n_in = upper(t) - upper(t - n_total);  // taps w with 0 <= t - w < n_total
-  T y = T(0);
-  if (!zero && n_in > 0) {
-    y = xc - tot / T(n_in);
-    if (!(fabs(y) <= T(PE_TMAX))) y = T(0);
-  }
-  orow[t] = y;
+  const int64_t v1 = min64(max64(t, WLO - 1), WHI);
+  const int64_t v2 = min64(max64(t - n_total, WLO - 1), WHI);
+  const int n_in = count[v1 - (WLO - 1)] - count[v2 - (WLO - 1)];
+  T y = xc - tot * T(recip[n_in]);
+  if (zero || n_in == 0 || !finite_val(y)) y = T(0);
+  return y;
 }
 
 // Per-piece walking state of a consumer thread that changes at chunk boundaries.
@@ -214,8 +208,9 @@ struct Walk {
 };
 
 // Ends group g (releases its oldest chunk) and opens group g + 1 (waits for its newest chunk).
-__device__ __noinline__ Walk next_group(Walk w, uint32_t bars, int lane, int c, int n_groups,
-                                        int64_t T0, int64_t t0, int64_t n_out, int64_t n_total) {
+__device__ __forceinline__ Walk next_group_inline(Walk w, uint32_t bars, int lane, int c,
+                                                  int n_groups, int64_t T0, int64_t t0,
+                                                  int64_t n_out, int64_t n_total) {
   if (w.g >= 0) {
     __syncwarp();
     if (lane == 0) {
@@ -248,6 +243,20 @@ __device__ __noinline__ Walk next_group(Walk w, uint32_t bars, int lane, int c, 
     w.mode = (interior && all_out) ? 1 : 2;
   }
   return w;
+}
+
+// With static grouping (U | M0) the boundary code appears M0 / U times in the unrolled block
+// and is inlined; with dynamic grouping it would appear M0 times, so it stays a call there.
+__device__ __noinline__ Walk next_group_call(Walk w, uint32_t bars, int lane, int c, int n_groups,
+                                             int64_t T0, int64_t t0, int64_t n_out,
+                                             int64_t n_total) {
+  return next_group_inline(w, bars, lane, c, n_groups, T0, t0, n_out, n_total);
+}
+__device__ __forceinline__ Walk next_group(Walk w, uint32_t bars, int lane, int c, int n_groups,
+                                           int64_t T0, int64_t t0, int64_t n_out,
+                                           int64_t n_total) {
+  if (STATIC_GROUPS) return next_group_inline(w, bars, lane, c, n_groups, T0, t0, n_out, n_total);
+  return next_group_call(w, bars, lane, c, n_groups, T0, t0, n_out, n_total);
 }
 
 extern "C" __global__ void __launch_bounds__(NT, PE_CTAS) parrm_filter_comb_e(const Args a) {
@@ -427,8 +436,9 @@ extern "C" __global__ void __launch_bounds__(NT, PE_CTAS) parrm_filter_comb_e(co
         if (w.mode == 1) {
           if (lane_stores) orow[w.t_out + js * D] = y;
         } else if (w.mode == 2) {
-          if (lane_stores)
-            edge_store(a.taps, orow, w.t_out + js * D, a.t0, a.n_out, a.n_total, xc, tot, zero);
+          const int64_t t = w.t_out + js * D;
+          if (lane_stores && t >= a.t0 && t < a.t0 + a.n_out)
+            orow[t] = edge_value(a.count, a.recip, t, a.n_total, xc, tot, zero);
         }
         ++k;
         bool boundary;

@@ -178,8 +178,16 @@ bool comb_e_shape(const FilterPlanHeader* hdr, const int32_t* terms, int dtype,
   if (ring_regs > 180) return false;
   s.ctas = ring_regs <= 76 ? 2 : 1;
   if (tune && tune->ctas_per_sm > 0) s.ctas = tune->ctas_per_sm;
-  // chunk: U steps of d samples, about 6 KB, a whole number of 16-byte units
-  int u = int((6400 + int64_t(s.d) * s.es / 2) / (int64_t(s.d) * s.es));
+  // chunk: U steps of d samples, a whole number of 16-byte units.  A divisor of M0 near 8 KB
+  // puts the chunk boundaries at fixed steps of the unrolled block (static grouping);
+  // otherwise about 6 KB with the boundary tracked at run time.
+  int u = 0;
+  for (int cand = 1; cand <= s.m[0]; ++cand) {
+    const int64_t bytes = int64_t(cand) * s.d * s.es;
+    if (s.m[0] % cand != 0 || bytes % 16 != 0 || bytes < 4096 || bytes > 12288) continue;
+    if (u == 0 || llabs(bytes - 8192) < llabs(int64_t(u) * s.d * s.es - 8192)) u = cand;
+  }
+  if (u == 0) u = int((6400 + int64_t(s.d) * s.es / 2) / (int64_t(s.d) * s.es));
   if (tune && tune->steps_per_chunk > 0) u = tune->steps_per_chunk;
   if (u < 1) u = 1;
   while ((int64_t(u) * s.d * s.es) % 16 != 0) ++u;
@@ -314,7 +322,8 @@ std::string comb_e_key(const CombEShape& s, int dev) {
 
 // Launches the specialised kernel (building it on first use).  PARRM_ERR_UNSUPPORTED means
 // "could not specialise here"; the caller falls back to the pre-built kernels.
-int launch_comb_e(const CombEShape& s, const void* d_x, void* d_out, const int32_t* d_taps,
+int launch_comb_e(const CombEShape& s, const void* d_x, void* d_out, const int32_t* d_count,
+                  const double* d_recip,
                   int64_t ld_x, int64_t x_t0, int64_t n_x, int64_t ld_out, int64_t t0,
                   int64_t n_out, int64_t n_total, int64_t n_chans, cudaStream_t stream,
                   int* regs_out) {
@@ -337,11 +346,12 @@ int launch_comb_e(const CombEShape& s, const void* d_x, void* d_out, const int32
   struct Args {
     const void* x;
     void* out;
-    const int32_t* taps;
+    const int32_t* count;
+    const double* recip;
     int64_t ld_x, x_t0, n_x, ld_out, t0, n_out, n_total, total_groups;
     int32_t groups_per_chan, pad;
   } a;
-  a.x = d_x; a.out = d_out; a.taps = d_taps;
+  a.x = d_x; a.out = d_out; a.count = d_count; a.recip = d_recip;
   a.ld_x = ld_x; a.x_t0 = x_t0; a.n_x = n_x;
   a.ld_out = ld_out; a.t0 = t0; a.n_out = n_out; a.n_total = n_total;
   const int64_t ch = k.chunk;

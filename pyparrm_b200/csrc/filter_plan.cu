@@ -185,17 +185,33 @@ bool best_comb(const int32_t* taps, int n, CombPlan* best) {
 
 extern "C" {
 
-size_t parrm_filter_plan_bytes(int32_t n_taps) {
-  return sizeof(parrm::FilterPlanHeader) +
-         (size_t(n_taps > 0 ? n_taps : 0) + parrm::kMaxTerms) * sizeof(int32_t);
+// blob layout: header | taps[n] | terms[kMaxTerms] | (8-byte aligned) recip[n + 1] | count[span + 2]
+static size_t plan_layout(const int32_t* h_taps, int32_t n_taps, size_t* recip_off, size_t* count_off) {
+  const size_t n = size_t(n_taps > 0 ? n_taps : 0);
+  size_t off = sizeof(parrm::FilterPlanHeader) + (n + parrm::kMaxTerms) * sizeof(int32_t);
+  off = (off + 7) & ~size_t(7);
+  if (recip_off) *recip_off = off;
+  off += (n + 1) * sizeof(double);
+  if (count_off) *count_off = off;
+  int64_t span = 0;
+  if (n > 0 && h_taps != nullptr) {
+    const int64_t lo = h_taps[0] < 0 ? h_taps[0] : 0;
+    const int64_t hi = h_taps[n - 1] > 0 ? h_taps[n - 1] : 0;
+    span = hi - lo;
+  }
+  off += size_t(span + 2) * sizeof(int32_t);
+  return (off + 15) & ~size_t(15);
+}
+
+size_t parrm_filter_plan_bytes(const int32_t* h_taps, int32_t n_taps) {
+  return plan_layout(h_taps, n_taps, nullptr, nullptr);
 }
 
 int parrm_filter_plan(const int32_t* h_taps, int32_t n_taps, int dtype, int strategy,
                       void* h_plan, size_t plan_bytes) {
   using namespace parrm;
   PARRM_REQUIRE(n_taps > 0 && h_taps != nullptr, "parrm_filter_plan: empty tap list");
-  PARRM_REQUIRE(h_plan != nullptr && plan_bytes >= parrm_filter_plan_bytes(n_taps),
-                "parrm_filter_plan: plan buffer too small");
+  PARRM_REQUIRE(h_plan != nullptr, "parrm_filter_plan: null plan buffer");
   PARRM_REQUIRE(dtype == PARRM_F64 || dtype == PARRM_F32, "parrm_filter_plan: bad dtype");
   PARRM_REQUIRE(strategy >= PARRM_PLAN_AUTO && strategy <= PARRM_PLAN_COMB,
                 "parrm_filter_plan: unknown strategy %d", strategy);
@@ -203,7 +219,12 @@ int parrm_filter_plan(const int32_t* h_taps, int32_t n_taps, int dtype, int stra
     PARRM_REQUIRE(h_taps[i] > h_taps[i - 1], "parrm_filter_plan: taps must be strictly ascending");
   PARRM_REQUIRE(h_taps[0] > -(1 << 30) && h_taps[n_taps - 1] < (1 << 30),
                 "parrm_filter_plan: tap offset out of range");
-  memset(h_plan, 0, parrm_filter_plan_bytes(n_taps));
+  size_t recip_off = 0, count_off = 0;
+  const size_t total = plan_layout(h_taps, n_taps, &recip_off, &count_off);
+  PARRM_REQUIRE(plan_bytes >= total, "parrm_filter_plan: plan buffer too small (%zu < %zu)",
+                plan_bytes, total);
+  PARRM_REQUIRE(total < (size_t(1) << 31), "parrm_filter_plan: tap window too wide");
+  memset(h_plan, 0, total);
   FilterPlanHeader* hdr = static_cast<FilterPlanHeader*>(h_plan);
   hdr->magic = kPlanMagic;
   hdr->version = kPlanVersion;
@@ -217,6 +238,22 @@ int parrm_filter_plan(const int32_t* h_taps, int32_t n_taps, int dtype, int stra
   hdr->cost_milli = n_taps * 1000;
   unsigned char* base = static_cast<unsigned char*>(h_plan);
   memcpy(base + hdr->taps_offset, h_taps, size_t(n_taps) * sizeof(int32_t));
+  {  // edge tables: in-range tap counts by lookup, reciprocals of the possible counts
+    hdr->recip_offset = int32_t(recip_off);
+    hdr->count_offset = int32_t(count_off);
+    hdr->total_bytes = int32_t(total);
+    double* recip = reinterpret_cast<double*>(base + recip_off);
+    recip[0] = 0.0;
+    for (int32_t i = 1; i <= n_taps; ++i) recip[i] = 1.0 / double(i);
+    int32_t* count = reinterpret_cast<int32_t*>(base + count_off);
+    const int64_t w_lo = h_taps[0] < 0 ? h_taps[0] : 0;
+    const int64_t w_hi = h_taps[n_taps - 1] > 0 ? h_taps[n_taps - 1] : 0;
+    int32_t i = 0;
+    for (int64_t v = w_lo - 1; v <= w_hi; ++v) {
+      while (i < n_taps && h_taps[i] <= v) ++i;
+      count[v - (w_lo - 1)] = i;
+    }
+  }
   if (strategy == PARRM_PLAN_GATHER) return PARRM_OK;
 
   CombPlan best;

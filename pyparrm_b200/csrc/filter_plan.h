@@ -19,7 +19,7 @@
 namespace parrm {
 
 constexpr uint32_t kPlanMagic = 0x4D525250u;  // "PRRM"
-constexpr uint32_t kPlanVersion = 2;
+constexpr uint32_t kPlanVersion = 3;
 constexpr int kMaxTerms = 120;                // structured terms passed as kernel parameters
 constexpr int kMaxBoxKinds = 2;
 
@@ -48,7 +48,13 @@ struct FilterPlanHeader {
   int32_t terms_offset;             // byte offset of int32 terms[]: boxes kind 0, boxes kind 1,
                                     // plus singles, minus singles
   int32_t cost_milli;               // modelled shared-memory loads per output x 1000
-  int32_t reserved[9];
+  // ---- recording edges (every kind) ----
+  int32_t count_offset;             // byte offset of int32 count[w_hi - w_lo + 2]:
+                                    //   count[v - (w_lo - 1)] = #{taps <= v},  w_lo - 1 <= v <= w_hi
+                                    //   (w_lo = min(w_min, 0), w_hi = max(w_max, 0))
+  int32_t recip_offset;             // byte offset of float64 recip[n_taps + 1]: 0, 1/1, 1/2, ...
+  int32_t total_bytes;              // size of the whole blob
+  int32_t reserved[6];
 };
 static_assert(sizeof(FilterPlanHeader) == 128, "plan header is 128 bytes");
 

@@ -99,9 +99,9 @@ if __name__ == "__main__":
     t0 = time.time()
     if "--no-parity" not in sys.argv:
         print("worst", parity())
-    tunings = [{}, {"steps_per_chunk": 2}, {"steps_per_chunk": 5}, {"steps_per_chunk": 8},
+    tunings = [{}, {"steps_per_chunk": 4}, {"steps_per_chunk": 10}, {"steps_per_chunk": 3},
                {"prefetch_chunks": 6}, {"prefetch_chunks": 2}, {"ctas_per_sm": 1},
-               {"steps_per_chunk": 5, "prefetch_chunks": 6}]
+               {"steps_per_chunk": 4, "ctas_per_sm": 1}]
     rows = timing("cfg2", 64, 1_200_000, tunings)
     rows += timing("cfg3", 64, 1_200_000, [{}])
     os.makedirs("gpurun_out", exist_ok=True)

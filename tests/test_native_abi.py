@@ -43,7 +43,8 @@ def test_argument_errors_are_reported_not_crashed():
     plan = np.zeros(4096, dtype=np.uint8)
     status = _native.lib.parrm_filter_plan(taps.ctypes.data, 3, 0, 0, plan.ctypes.data, 4096)
     assert status == 1 and "ascending" in _native.last_error()
-    assert _native.lib.parrm_filter_plan_bytes(160) >= 32 + 160 * 4
+    taps = np.arange(1, 161, dtype=np.int32)
+    assert _native.lib.parrm_filter_plan_bytes(taps.ctypes.data, 160) >= 128 + 160 * 4
 
 
 def test_launch_accounting_follows_the_shape():
