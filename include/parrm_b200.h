@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PARRM_B200_ABI_VERSION 4
+#define PARRM_B200_ABI_VERSION 5
 
 typedef enum {
   PARRM_OK = 0,
@@ -149,9 +149,9 @@ int parrm_build_taps(double period, double period_half_width, int64_t filter_hal
  *
  * Every tap has the same weight (parrm.py:829), so the planner may regroup the tap set into
  * windowed stride-d sums ("comb boxes") plus single taps -- an exact identity over which
- * offsets are summed, pyparrm_b200/csrc/filter_plan.h -- which the strip kernel evaluates with
- * ~10x fewer shared-memory loads than one load per tap.  parrm_filter_plan_info() exposes the
- * decomposition (tests expand it back into the tap set).
+ * offsets are summed, pyparrm_b200/csrc/filter_plan.h -- which the run-time specialised kernel
+ * evaluates with ~10x fewer shared-memory loads than one load per tap.
+ * parrm_filter_plan_info() exposes the decomposition (tests expand it back into the tap set).
  * ---------------------------------------------------------------------- */
 size_t parrm_filter_plan_bytes(const int32_t* h_taps, int32_t n_taps);
 int parrm_filter_plan(const int32_t* h_taps, int32_t n_taps, int dtype, int strategy,
@@ -168,13 +168,13 @@ int parrm_filter_apply(const void* d_x, int64_t ld_x, int64_t x_t0, int64_t n_x,
 
 /* Which kernel evaluates the plan.  AUTO picks, for comb plans, a kernel SPECIALISED for the
  * plan at run time (NVRTC, sm_100a: stride, box lengths and tap offsets are immediates; built
- * once per plan and device, about a second) when the call is large enough to be worth it or
- * the kernel already exists, else the pre-built STRIP kernels, else the GATHER.  All of them
- * compute the same tap sum; they differ in floating-point association only. */
+ * once per plan and device, about a second) when the call is large enough (2^24
+ * channel-samples) to be worth it or the kernel already exists, else the pre-built GATHER
+ * (one shared-memory load per tap).  Both compute the same tap sum; they differ in
+ * floating-point association only.  (Value 2 was the round-1 strip kernel, removed.) */
 typedef enum {
   PARRM_FILTER_KERNEL_AUTO = 0,
   PARRM_FILTER_KERNEL_GATHER = 1,
-  PARRM_FILTER_KERNEL_STRIP = 2,
   PARRM_FILTER_KERNEL_SPECIALISED = 3
 } parrm_filter_kernel_t;
 

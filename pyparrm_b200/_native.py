@@ -19,9 +19,9 @@ F64, F32 = 0, 1
 DIR_BOTH, DIR_PAST, DIR_FUTURE = 0, 1, 2
 DIRECTIONS = {"both": DIR_BOTH, "past": DIR_PAST, "future": DIR_FUTURE}
 MAX_BANDWIDTH = 23
-ABI_VERSION = 4
+ABI_VERSION = 5
 PLAN_AUTO, PLAN_GATHER, PLAN_COMB = 0, 1, 2
-KERNEL_AUTO, KERNEL_GATHER, KERNEL_STRIP, KERNEL_SPECIALISED = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_GATHER, KERNEL_SPECIALISED = 0, 1, 3
 
 
 class FilterOptions(ctypes.Structure):
@@ -139,7 +139,7 @@ def device_count() -> int:
 def plan_filter(taps, dtype: int = F64, strategy: int = PLAN_AUTO):
     """Build a filter plan on the host; returns ``(plan_bytes, description)``.
 
-    ``description`` is the decomposition the strip kernel evaluates: ``kind`` (0 gather,
+    ``description`` is the decomposition the run-time specialised kernel evaluates: ``kind`` (0 gather,
     1 comb), ``stride``, ``windows`` (box lengths), ``boxes`` (one offset array per length),
     ``plus`` / ``minus`` single taps, ``centre`` and the modelled ``cost`` in loads per output.
     Pure host work: usable without a GPU.

@@ -11,10 +11,10 @@
 // and the comb becomes a running sum of E_k along the chain t, t+d, t+2d, ...:
 //     S_k[t] = sum_{q<M_k} E_k[t - q d],     S_k[t + d] = S_k[t] + E_k[t + d] - E_k[t + d - M_k d].
 // One thread owns one chain (one residue of t mod d).  It keeps the last M_k values of E_k in
-// REGISTERS (statically indexed: the step loop is unrolled M_0 deep), so per output the shared
+// REGISTERS (statically indexed: the step loop is unrolled >= M_0 deep), so per output the shared
 // memory pipe sees only the NB_0 + NB_1 pattern loads, the single taps and x[t] -- for the
 // cfg2 filter (160 taps) 12 loads instead of 160, and no intermediate array at all.  The sums
-// are re-added from the register ring every M_0 steps, which bounds rounding drift.
+// are re-added from the register rings once per unrolled block, which bounds rounding drift.
 //
 // Data movement: a persistent CTA walks a strip of consecutive chunks (U*d samples) of one
 // channel.  A producer warp streams chunks HBM -> shared ring with TMA bulk copies
@@ -25,8 +25,8 @@
 // go straight from registers to HBM, 32 consecutive samples per warp store.
 //
 // Non-finite samples: an output whose tap window (or own sample) holds a NaN/Inf is 0, as the
-// reference's isfinite -> 0 replacement (parrm.py:869) intends; the bad pattern value is
-// dropped from the ring, so outputs past the window are exact again.
+// reference's isfinite -> 0 replacement (parrm.py:869) intends (run_block: the sums are re-added
+// from the rings while the bad value is inside the window, so outputs past it are exact again).
 #pragma once
 
 #ifdef __CUDACC_RTC__
@@ -55,17 +55,14 @@ typedef unsigned long long uintptr_t;
 #define PE_NMINUS 0
 #define PE_MINUS 0
 #define PE_CENTRE -1
-#define PE_U 5
-#define PE_PF 4
+#define PE_U 10
+#define PE_PF 2
 #define PE_NTAPS 160
 #define PE_WLO -2000
 #define PE_WHI 2000
 #define PE_BACK 108
 #define PE_FWD 2000
 #define PE_CTAS 2
-#endif
-#ifndef PE_TMAX  // largest finite value of PE_T
-#define PE_TMAX 1.7976931348623157e308
 #endif
 
 namespace parrm_e {
@@ -95,12 +92,13 @@ constexpr int HB = (BACK + CH - 1) / CH;         // chunks behind the current on
 constexpr int HF = (FWD + CH - 1) / CH;          // chunks ahead
 constexpr int MIR = HB + HF;                     // mirrored ring chunks
 constexpr int Q = HB + HF + 1 + PF;              // ring chunks
-constexpr int NPG = (M0 + U - 1) / U;            // priming groups (fill the register rings)
+constexpr int GPB = (M0 + U - 1) / U;            // groups (chunks) per unrolled block
+constexpr int B = GPB * U;                       // steps per unrolled block (>= M0)
+constexpr int NPG = GPB;                         // priming groups: one block fills the rings
 constexpr int NW = (D + 31) / 32;                // consumer warps
 constexpr int NT = NW * 32 + 32;                 // + one producer warp
 constexpr int BAR_BYTES = ((2 * Q * 8 + 127) / 128) * 128;
 constexpr int SMEM_BYTES = BAR_BYTES + (Q + MIR) * CH * ES;
-constexpr bool STATIC_GROUPS = (M0 % U) == 0;  // chunk boundaries at fixed steps of the block
 static_assert((CH * ES) % 16 == 0, "chunk must be a whole number of 16-byte units");
 static_assert(M0 >= M1 && M0 >= 1, "box lengths ordered");
 
@@ -133,6 +131,8 @@ struct Args {
   int64_t total_groups;  // n_chans * groups_per_chan
   int32_t groups_per_chan;
   int32_t pad;
+  T neg_inv_n;  // -1 / NTAPS   (kernel parameters: FP64 instructions take them as constant-bank
+  T t_max;      // largest finite T           operands, so they occupy no registers in the loop)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -177,7 +177,6 @@ __device__ __forceinline__ int64_t floor_div(int64_t a, int64_t b) {
 }
 __device__ __forceinline__ int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
 __device__ __forceinline__ int64_t max64(int64_t a, int64_t b) { return a > b ? a : b; }
-__device__ __forceinline__ bool finite_val(T v) { return fabs(v) <= T(PE_TMAX); }
 
 // Recording edges (outputs whose tap window leaves [0, n_total), and chunks only partly inside
 // the requested output range): mean over the in-range taps, parrm.py:861-866.  The number of
@@ -186,77 +185,172 @@ __device__ __forceinline__ bool finite_val(T v) { return fabs(v) <= T(PE_TMAX); 
 // division: this sits in the unrolled step loop and must stay small).
 __device__ __forceinline__ T edge_value(const int32_t* __restrict__ count,
                                         const T2* __restrict__ recip, int64_t t, int64_t n_total,
-                                        T xc, T tot, bool zero) {
+                                        T xc, T tot) {
   const int64_t v1 = min64(max64(t, WLO - 1), WHI);
   const int64_t v2 = min64(max64(t - n_total, WLO - 1), WHI);
   const int n_in = count[v1 - (WLO - 1)] - count[v2 - (WLO - 1)];
   T y = xc - tot * T(recip[n_in]);
-  if (zero || n_in == 0 || !finite_val(y)) y = T(0);
+  if (n_in == 0) y = T(0);
   return y;
 }
 
-// Per-piece walking state of a consumer thread that changes at chunk boundaries.
+// A consumer thread's position in the chunk sequence of its piece.
 struct Walk {
-  int pb;          // byte offset (from smem_raw) of the sample HB*CH before the current output
-  int rslot;       // oldest live ring slot (next to release)
-  int fslot;       // next ring slot to wait for
-  uint32_t fphase; // parity of that fill
-  int g;           // group (chunk of outputs) inside the piece; -1 before the first
-  int mode;        // 0 priming (no outputs), 1 interior, 2 recording edge / partial range
-  int more;        // 0 once the piece is finished
-  int64_t t_out;   // global time of the thread's output at the first step of the group
+  int pb;           // byte offset (from smem_raw) of the sample HB*CH before the group's first output
+  int rslot;        // oldest live ring slot (next to release)
+  int fslot;        // next ring slot to wait for
+  uint32_t fphase;  // parity of that fill
 };
 
-// Ends group g (releases its oldest chunk) and opens group g + 1 (waits for its newest chunk).
-__device__ __forceinline__ Walk next_group_inline(Walk w, uint32_t bars, int lane, int c,
-                                                  int n_groups, int64_t T0, int64_t t0,
-                                                  int64_t n_out, int64_t n_total) {
-  if (w.g >= 0) {
-    __syncwarp();
-    if (lane == 0) {
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + (Q + w.rslot) * 8)
-                   : "memory");
-    }
-    w.pb += CH * ES;
-    if (++w.rslot == Q) {
-      w.rslot = 0;
-      w.pb -= Q * CH * ES;
-    }
-  }
-  ++w.g;
-  if (w.g == n_groups) {
-    w.more = 0;
-    return w;
-  }
+// Opens a group: its newest chunk has landed.
+__device__ __forceinline__ void group_begin(Walk& w, uint32_t bars) {
   mbar_wait(bars + w.fslot * 8, w.fphase);
   if (++w.fslot == Q) {
     w.fslot = 0;
     w.fphase ^= 1u;
   }
-  const int64_t Tn = T0 + int64_t(w.g) * CH;  // T0: global time of the piece's first group
-  w.t_out = Tn + c;
-  if (w.g < NPG) {
-    w.mode = 0;
-  } else {
-    const bool interior = (Tn - WHI >= 0) && (Tn + CH - WLO <= n_total);
-    const bool all_out = (Tn >= t0) && (Tn + CH <= t0 + n_out);
-    w.mode = (interior && all_out) ? 1 : 2;
+}
+// Closes a group: its oldest chunk is released to the producer.
+__device__ __forceinline__ void group_end(Walk& w, uint32_t bars, int lane) {
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + (Q + w.rslot) * 8)
+                 : "memory");
   }
-  return w;
+  w.pb += CH * ES;
+  if (++w.rslot == Q) {
+    w.rslot = 0;
+    w.pb -= Q * CH * ES;
+  }
 }
 
-// With static grouping (U | M0) the boundary code appears M0 / U times in the unrolled block
-// and is inlined; with dynamic grouping it would appear M0 times, so it stays a call there.
-__device__ __noinline__ Walk next_group_call(Walk w, uint32_t bars, int lane, int c, int n_groups,
-                                             int64_t T0, int64_t t0, int64_t n_out,
-                                             int64_t n_total) {
-  return next_group_inline(w, bars, lane, c, n_groups, T0, t0, n_out, n_total);
+// Register rings of one chain: the last M_k pattern values, statically indexed.  The step
+// loop is unrolled B = U * ceil(M0 / U) deep (a whole number of chunks, so chunk boundaries
+// sit at fixed places of the unrolled code); ring position s of a block is written at step s
+// and read again M_k steps later, so only M_0 + M_1 entries are live at any time.
+struct Rings {
+  T r0[B];
+  T r1[NK > 1 ? B : 1];
+  T S0, S1;
+};
+
+// sum of the last M_k ring entries, the newest at position s (static after unrolling)
+__device__ __forceinline__ T ring_sum0(const Rings& r, int s) {
+  T a = r.r0[s];
+#pragma unroll
+  for (int i = 1; i < M0; ++i) a += r.r0[(s + B - i) % B];
+  return a;
 }
-__device__ __forceinline__ Walk next_group(Walk w, uint32_t bars, int lane, int c, int n_groups,
-                                           int64_t T0, int64_t t0, int64_t n_out,
-                                           int64_t n_total) {
-  if (STATIC_GROUPS) return next_group_inline(w, bars, lane, c, n_groups, T0, t0, n_out, n_total);
-  return next_group_call(w, bars, lane, c, n_groups, T0, t0, n_out, n_total);
+__device__ __forceinline__ T ring_sum1(const Rings& r, int s) {
+  if (NK < 2) return T(0);
+  T a = r.r1[s];
+#pragma unroll
+  for (int i = 1; i < M1; ++i) a += r.r1[(s + B - i) % B];
+  return a;
+}
+
+// One block of B steps (GPB groups) of one chain.  FAST: every output of the block is an
+// interior output inside the requested range -- no per-group mode, no edge code.  Otherwise
+// groups may be priming groups (no outputs), recording edges or partial ranges, and the piece
+// may end inside the block.  Returns the number of groups done.
+//
+// Non-finite samples: the fast path only tests the finished output.  A NaN/Inf that entered a
+// running sum keeps it non-finite, so the test fails on every step until the bad pattern
+// value has left the ring; on those (rare) steps the sums are re-added from the rings, which
+// makes the first output past the window exact again and leaves the ones inside it 0.
+template <bool FAST>
+__device__ __forceinline__ int run_block(Rings& r, Walk& w, const Args& a,
+                                         const unsigned char* const smem, uint32_t bars,
+                                         int lane, int c, bool lane_stores, T* const orow,
+                                         int64_t Tb, int g, int n_groups) {
+  const T neg_inv_n = a.neg_inv_n;
+  const T t_max = a.t_max;
+  T* const op = orow + Tb + c;  // output of step 0 of the block
+  int done = 0;
+#pragma unroll
+  for (int gi = 0; gi < GPB; ++gi) {
+    if (!FAST && g + gi >= n_groups) break;
+    group_begin(w, bars);
+    int mode = 1;  // 0 priming (no outputs), 1 interior, 2 recording edge / partial range
+    if (!FAST) {
+      const int64_t Tn = Tb + int64_t(gi) * CH;
+      const bool interior = (Tn - WHI >= 0) && (Tn + CH - WLO <= a.n_total);
+      const bool all_out = (Tn >= a.t0) && (Tn + CH <= a.t0 + a.n_out);
+      mode = (g + gi < NPG) ? 0 : ((interior && all_out) ? 1 : 2);
+    }
+    const unsigned char* const p = smem + w.pb;
+#pragma unroll
+    for (int js = 0; js < U; ++js) {
+      const int s = gi * U + js;
+      auto ld = [&](int off) {  // sample at (current output time - off)
+        return *reinterpret_cast<const T*>(p + (HB * CH + js * D - off) * ES);
+      };
+      // leaving values first: their registers are free for the new pattern values
+      r.S0 -= r.r0[(s + B - M0) % B];
+      if (NK > 1) r.S1 -= r.r1[(s + B - M1) % B];
+      T e0 = ld(off0(0));  // two partial sums: shorter dependent chains
+      if (NB0 > 1) {
+        T e0b = ld(off0(1));
+#pragma unroll
+        for (int b = 2; b < NB0; ++b) {
+          if (b & 1) e0b += ld(off0(b)); else e0 += ld(off0(b));
+        }
+        e0 += e0b;
+      }
+      r.r0[s] = e0;
+      r.S0 += e0;
+      T tot = r.S0;
+      if (NK > 1) {
+        T e1 = ld(off1(0));
+        if (NB1 > 1) {
+          T e1b = ld(off1(1));
+#pragma unroll
+          for (int b = 2; b < NB1; ++b) {
+            if (b & 1) e1b += ld(off1(b)); else e1 += ld(off1(b));
+          }
+          e1 += e1b;
+        }
+        r.r1[s] = e1;
+        r.S1 += e1;
+        tot += r.S1;
+      }
+      T single = T(0);
+      if (NPLUS > 0) {
+        single = ld(plus_tap(0));
+#pragma unroll
+        for (int i = 1; i < NPLUS; ++i) single += ld(plus_tap(i));
+      }
+#pragma unroll
+      for (int i = 0; i < NMINUS; ++i) single -= ld(minus_tap(i));
+      const T xc = ld(0);
+      if (CENTRE != 0) single = fma(T(CENTRE), xc, single);
+      if (NPLUS > 0 || NMINUS > 0 || CENTRE != 0) tot += single;
+      if (FAST) {
+        T y = fma(tot, neg_inv_n, xc);
+        if (__builtin_expect(!(fabs(y) <= t_max), 0)) {
+          r.S0 = ring_sum0(r, s);
+          r.S1 = ring_sum1(r, s);
+          y = fma(r.S0 + r.S1 + single, neg_inv_n, xc);
+          if (!(fabs(y) <= t_max)) y = T(0);
+        }
+        if (lane_stores) op[s * D] = y;
+      } else if (mode != 0) {
+        const int64_t t = Tb + c + int64_t(s) * D;
+        T y = mode == 1 ? fma(tot, neg_inv_n, xc) : edge_value(a.count, a.recip, t, a.n_total, xc, tot);
+        if (__builtin_expect(!(fabs(y) <= t_max), 0)) {
+          r.S0 = ring_sum0(r, s);
+          r.S1 = ring_sum1(r, s);
+          tot = r.S0 + r.S1 + single;
+          y = mode == 1 ? fma(tot, neg_inv_n, xc) : edge_value(a.count, a.recip, t, a.n_total, xc, tot);
+          if (!(fabs(y) <= t_max)) y = T(0);
+        }
+        if (lane_stores && t >= a.t0 && t < a.t0 + a.n_out) op[s * D] = y;
+      }
+    }
+    group_end(w, bars, lane);
+    ++done;
+  }
+  return done;
 }
 
 extern "C" __global__ void __launch_bounds__(NT, PE_CTAS) parrm_filter_comb_e(const Args a) {
@@ -350,113 +444,29 @@ extern "C" __global__ void __launch_bounds__(NT, PE_CTAS) parrm_filter_comb_e(co
         fphase ^= 1u;
       }
     }
-    T r0[M0];
-    T r1[NK > 1 ? M0 : 1];
+    Rings r;
 #pragma unroll
-    for (int s = 0; s < M0; ++s) r0[s] = T(0);
+    for (int s = 0; s < B; ++s) r.r0[s] = T(0);
 #pragma unroll
-    for (int s = 0; s < (NK > 1 ? M0 : 1); ++s) r1[s] = T(0);
-    const T inv_n = T(1) / T(NTAPS);
-    const int64_t T0 = gamma + (n_first - NPG) * int64_t(CH);
+    for (int s = 0; s < (NK > 1 ? B : 1); ++s) r.r1[s] = T(0);
+    const int64_t T0 = gamma + (n_first - NPG) * int64_t(CH);  // time of the piece's first group
     Walk w;
     w.pb = BAR_BYTES + (rslot * CH + c) * ES;
     w.rslot = rslot;
     w.fslot = fslot;
     w.fphase = fphase;
-    w.g = -1;
-    w.mode = 0;
-    w.more = 1;
-    w.t_out = 0;
-    w = next_group(w, bars, lane, c, n_groups, T0, a.t0, a.n_out, a.n_total);
-    int k = 0;       // steps done in this piece
-    int k_dead = 0;  // outputs of steps < k_dead have a non-finite sample in their window
-    int j = 0;       // step inside the group (dynamic grouping only)
-
-    while (w.more) {
+    for (int g = 0; g < n_groups;) {
+      const int64_t Tb = T0 + int64_t(g) * CH;
       // fresh sums from the rings (bounds the drift of the running update)
-      T S0 = r0[0], S1 = T(0);
-#pragma unroll
-      for (int s = 1; s < M0; ++s) S0 += r0[s];
-      if (NK > 1) {
-        S1 = r1[M0 - M1];
-#pragma unroll
-        for (int s = M0 - M1 + 1; s < M0; ++s) S1 += r1[s];
-      }
-#pragma unroll
-      for (int s = 0; s < M0; ++s) {
-        // with U | M0 the position inside the group is static and folds into the immediates
-        const int js = STATIC_GROUPS ? (s % U) : 0;
-        const unsigned char* const p = smem_raw + w.pb;
-        auto ld = [&](int off) {  // sample at (current output time - off)
-          return *reinterpret_cast<const T*>(p + (HB * CH + js * D - off) * ES);
-        };
-        T e0 = ld(off0(0));  // two partial sums: shorter dependent chains
-        if (NB0 > 1) {
-          T e0b = ld(off0(1));
-#pragma unroll
-          for (int b = 2; b < NB0; ++b) {
-            if (b & 1) e0b += ld(off0(b)); else e0 += ld(off0(b));
-          }
-          e0 += e0b;
-        }
-        if (!finite_val(e0)) {  // dropped from the sums; its window's outputs are 0
-          e0 = T(0);
-          k_dead = max(k_dead, k + M0);
-        }
-        S0 += e0 - r0[s];
-        r0[s] = e0;
-        T tot = S0;
-        if (NK > 1) {
-          T e1 = ld(off1(0));
-          if (NB1 > 1) {
-            T e1b = ld(off1(1));
-#pragma unroll
-            for (int b = 2; b < NB1; ++b) {
-              if (b & 1) e1b += ld(off1(b)); else e1 += ld(off1(b));
-            }
-            e1 += e1b;
-          }
-          if (!finite_val(e1)) {
-            e1 = T(0);
-            k_dead = max(k_dead, k + M1);
-          }
-          S1 += e1 - r1[(s + M0 - M1) % M0];
-          r1[s] = e1;
-          tot += S1;
-        }
-#pragma unroll
-        for (int i = 0; i < NPLUS; ++i) tot += ld(plus_tap(i));
-#pragma unroll
-        for (int i = 0; i < NMINUS; ++i) tot -= ld(minus_tap(i));
-        const T xc = ld(0);
-        if (CENTRE != 0) tot = fma(T(CENTRE), xc, tot);
-        T y = fma(-tot, inv_n, xc);
-        const bool zero = !finite_val(y) || (k < k_dead);
-        if (zero) y = T(0);
-        if (w.mode == 1) {
-          if (lane_stores) orow[w.t_out + js * D] = y;
-        } else if (w.mode == 2) {
-          const int64_t t = w.t_out + js * D;
-          if (lane_stores && t >= a.t0 && t < a.t0 + a.n_out)
-            orow[t] = edge_value(a.count, a.recip, t, a.n_total, xc, tot, zero);
-        }
-        ++k;
-        bool boundary;
-        if (STATIC_GROUPS) {
-          boundary = (s % U) == U - 1;
-        } else {
-          w.pb += D * ES;
-          w.t_out += D;
-          boundary = ++j == U;
-        }
-        if (boundary) {
-          if (!STATIC_GROUPS) {
-            j = 0;
-            w.pb -= CH * ES;  // next_group advances by one chunk
-          }
-          w = next_group(w, bars, lane, c, n_groups, T0, a.t0, a.n_out, a.n_total);
-          if (!w.more) break;
-        }
+      r.S0 = ring_sum0(r, B - 1);
+      r.S1 = ring_sum1(r, B - 1);
+      const bool fast = g >= NPG && g + GPB <= n_groups && Tb - WHI >= 0 &&
+                        Tb + int64_t(B) * D - WLO <= a.n_total && Tb >= a.t0 &&
+                        Tb + int64_t(B) * D <= a.t0 + a.n_out;
+      if (fast) {
+        g += run_block<true>(r, w, a, smem_raw, bars, lane, c, lane_stores, orow, Tb, g, n_groups);
+      } else {
+        g += run_block<false>(r, w, a, smem_raw, bars, lane, c, lane_stores, orow, Tb, g, n_groups);
       }
     }
     rslot = w.rslot;

@@ -11,6 +11,7 @@
 #include <dlfcn.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <string>
@@ -134,21 +135,22 @@ std::string join(const int32_t* v, int n) {
 // pattern-first kernel handles (the caller then keeps the strip kernels).
 bool comb_e_shape(const FilterPlanHeader* hdr, const int32_t* terms, int dtype,
                   const FilterTuning* tune, CombEShape* out) {
-  if (hdr->kind != kPlanComb || hdr->n_kinds < 1 || hdr->n_kinds > 2) return false;
+  const FilterPlanHeader* sec = hdr;
+  if (hdr->kind != kPlanComb || sec->n_kinds < 1 || sec->n_kinds > 2) return false;
   CombEShape s;
   memset(&s, 0, sizeof(s));
   s.es = dtype == PARRM_F64 ? 8 : 4;
-  s.d = hdr->stride;
-  s.nk = hdr->n_kinds;
-  const int nb[2] = {hdr->n_box[0], hdr->n_kinds > 1 ? hdr->n_box[1] : 0};
+  s.d = sec->stride;
+  s.nk = sec->n_kinds;
+  const int nb[2] = {sec->n_box[0], sec->n_kinds > 1 ? sec->n_box[1] : 0};
   int first = 0;  // kind with the longer box goes first
-  if (s.nk == 2 && hdr->window[1] > hdr->window[0]) first = 1;
+  if (s.nk == 2 && sec->window[1] > sec->window[0]) first = 1;
   const int32_t* box[2] = {terms, terms + nb[0]};
-  s.m[0] = hdr->window[first];
+  s.m[0] = sec->window[first];
   s.nb[0] = nb[first];
   s.off[0] = box[first];
   if (s.nk == 2) {
-    s.m[1] = hdr->window[1 - first];
+    s.m[1] = sec->window[1 - first];
     s.nb[1] = nb[1 - first];
     s.off[1] = box[1 - first];
   } else {
@@ -156,11 +158,11 @@ bool comb_e_shape(const FilterPlanHeader* hdr, const int32_t* terms, int dtype,
     s.nb[1] = 0;
     s.off[1] = nullptr;
   }
-  s.n_plus = hdr->n_plus;
-  s.n_minus = hdr->n_minus;
+  s.n_plus = sec->n_plus;
+  s.n_minus = sec->n_minus;
   s.plus = terms + nb[0] + nb[1];
   s.minus = s.plus + s.n_plus;
-  s.centre = hdr->centre;
+  s.centre = sec->centre;
   s.n_taps = hdr->n_taps;
   s.w_lo = hdr->w_min < 0 ? hdr->w_min : 0;
   s.w_hi = hdr->w_max > 0 ? hdr->w_max : 0;
@@ -172,42 +174,53 @@ bool comb_e_shape(const FilterPlanHeader* hdr, const int32_t* terms, int dtype,
   }
   s.back = hi;
   s.fwd = -lo;
-  if (s.d < 64 || s.d > 992) return false;
+  if (s.d < kPatternFirstMinStride || s.d > kPatternFirstMaxStride) return false;
   if (n_all > 96 || s.nb[0] < 1) return false;
+  // Occupancy first, then chunk size.  Measured at the cfg2 shape (fraction of the HBM
+  // roofline): two CTAs per SM 64 % with 16 KB chunks, 57 % with 8 KB, 54 % with 6 KB; one CTA
+  // per SM 37-51 %.  Two CTAs per SM need the register rings (live: M0 + M1 values) to leave
+  // ~50 registers for the rest of the step inside the per-thread budget at that occupancy,
+  // and ring + mirror chunks inside half the shared memory.  A chunk is U steps of d samples,
+  // a whole number of 16-byte units; the step loop is unrolled B = U * ceil(M0 / U) deep.
   const int ring_regs = (s.m[0] + (s.nk > 1 ? s.m[1] : 0)) * (s.es / 4);
-  if (ring_regs > 180) return false;
-  s.ctas = ring_regs <= 76 ? 2 : 1;
-  if (tune && tune->ctas_per_sm > 0) s.ctas = tune->ctas_per_sm;
-  // chunk: U steps of d samples, a whole number of 16-byte units.  A divisor of M0 near 8 KB
-  // puts the chunk boundaries at fixed steps of the unrolled block (static grouping);
-  // otherwise about 6 KB with the boundary tracked at run time.
-  int u = 0;
-  for (int cand = 1; cand <= s.m[0]; ++cand) {
-    const int64_t bytes = int64_t(cand) * s.d * s.es;
-    if (s.m[0] % cand != 0 || bytes % 16 != 0 || bytes < 4096 || bytes > 12288) continue;
-    if (u == 0 || llabs(bytes - 8192) < llabs(int64_t(u) * s.d * s.es - 8192)) u = cand;
-  }
-  if (u == 0) u = int((6400 + int64_t(s.d) * s.es / 2) / (int64_t(s.d) * s.es));
-  if (tune && tune->steps_per_chunk > 0) u = tune->steps_per_chunk;
-  if (u < 1) u = 1;
-  while ((int64_t(u) * s.d * s.es) % 16 != 0) ++u;
-  const int pf_first = (tune && tune->prefetch_chunks > 0) ? tune->prefetch_chunks : 4;
-  // fewer chunks in flight first, then one CTA per SM (twice the shared memory each)
-  for (int ctas = s.ctas; ctas >= 1; --ctas) {
+  const int threads = ((s.d + 31) / 32) * 32 + 32;
+  auto reg_budget = [&](int ctas) { return std::min(255, (65536 / (ctas * threads)) / 8 * 8); };
+  if (ring_regs + 52 > reg_budget(1)) return false;
+  int ctas_first = ring_regs + 60 <= reg_budget(2) ? 2 : 1;  // 52 spills at the cfg3 shape
+  if (tune && tune->ctas_per_sm > 0) ctas_first = tune->ctas_per_sm;
+  const int pf_max = (tune && tune->prefetch_chunks > 0) ? tune->prefetch_chunks : 4;
+  const int pf_min = std::min(pf_max, 2);
+  auto smem_for = [&](int u, int pf) {
+    const int64_t ch = int64_t(u) * s.d;
+    const int64_t hb = (s.back + ch - 1) / ch, hf = (s.fwd + ch - 1) / ch;
+    const int64_t q = hb + hf + 1 + pf;
+    return ((2 * q * 8 + 127) / 128) * 128 + (q + hb + hf) * ch * s.es;
+  };
+  auto usable = [&](int u) {
+    return u >= 1 && (int64_t(u) * s.d * s.es) % 16 == 0 && (s.m[0] + u - 1) / u * u <= 64;
+  };
+  for (int ctas = ctas_first; ctas >= 1; --ctas) {
     const int64_t budget = int64_t(227) * 1024 / ctas - 1024;
-    for (int pf = pf_first; pf >= 2; --pf) {
-      const int64_t ch = int64_t(u) * s.d;
-      const int64_t hb = (s.back + ch - 1) / ch, hf = (s.fwd + ch - 1) / ch;
-      const int64_t q = hb + hf + 1 + pf;
-      const int64_t smem = ((2 * q * 8 + 127) / 128) * 128 + (q + hb + hf) * ch * s.es;
-      if (smem > budget) continue;
-      s.smem_bytes = int(smem);
-      s.ctas = ctas;
-      s.u = u;
-      s.pf = pf;
-      *out = s;
-      return true;
+    int u = 0;
+    if (tune && tune->steps_per_chunk > 0) {
+      u = tune->steps_per_chunk;
+      if (!usable(u) || smem_for(u, pf_min) > budget) u = 0;
+    } else {
+      const int u_hi = int(std::max<int64_t>(1, 20480 / (int64_t(s.d) * s.es)));
+      for (int cand = u_hi; cand >= 1 && u == 0; --cand)  // largest chunk <= 20 KB that fits
+        if (usable(cand) && smem_for(cand, pf_min) <= budget) u = cand;
+      for (int cand = 1; cand <= 64 && u == 0; ++cand)    // stride alone exceeds 20 KB
+        if (usable(cand) && smem_for(cand, pf_min) <= budget) u = cand;
     }
+    if (u == 0) continue;
+    int pf = pf_min;
+    while (pf < pf_max && smem_for(u, pf + 1) <= budget) ++pf;
+    s.smem_bytes = int(smem_for(u, pf));
+    s.ctas = ctas;
+    s.u = u;
+    s.pf = pf;
+    *out = s;
+    return true;
   }
   return false;
 }
@@ -222,7 +235,6 @@ static int compile_cubin(const CombEShape& s, std::vector<char>* cubin) {
   std::vector<std::string> opts = {
       "--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo",
       std::string("-DPE_T=") + (s.es == 8 ? "double" : "float"),
-      std::string("-DPE_TMAX=") + (s.es == 8 ? "1.7976931348623157e308" : "3.402823466e38f"),
       "-DPE_D=" + std::to_string(s.d), "-DPE_NK=" + std::to_string(s.nk),
       "-DPE_M0=" + std::to_string(s.m[0]), "-DPE_M1=" + std::to_string(s.m[1]),
       "-DPE_NB0=" + std::to_string(s.nb[0]), "-DPE_NB1=" + std::to_string(s.nb[1]),
@@ -350,6 +362,7 @@ int launch_comb_e(const CombEShape& s, const void* d_x, void* d_out, const int32
     const double* recip;
     int64_t ld_x, x_t0, n_x, ld_out, t0, n_out, n_total, total_groups;
     int32_t groups_per_chan, pad;
+    unsigned char consts[16];  // T neg_inv_n, t_max in the kernel's element type
   } a;
   a.x = d_x; a.out = d_out; a.count = d_count; a.recip = d_recip;
   a.ld_x = ld_x; a.x_t0 = x_t0; a.n_x = n_x;
@@ -358,6 +371,14 @@ int launch_comb_e(const CombEShape& s, const void* d_x, void* d_out, const int32
   a.groups_per_chan = int32_t(ceil_div(n_out + ch - 1, ch));
   a.total_groups = n_chans * int64_t(a.groups_per_chan);
   a.pad = 0;
+  memset(a.consts, 0, sizeof(a.consts));
+  if (s.es == 8) {
+    const double v[2] = {-1.0 / double(s.n_taps), 1.7976931348623157e308};
+    memcpy(a.consts, v, sizeof(v));
+  } else {
+    const float v[2] = {-1.0f / float(s.n_taps), 3.402823466e38f};
+    memcpy(a.consts, v, sizeof(v));
+  }
   // one strip per resident CTA; a strip is at least 4x its priming so the warm-up of the
   // register rings stays a small fraction of the work
   const int64_t resident = int64_t(kNumSMs) * k.ctas_per_sm;

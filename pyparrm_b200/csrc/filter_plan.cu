@@ -21,10 +21,6 @@ struct CombPlan {
   int n_terms() const { return int(box[0].size() + box[1].size() + plus.size() + minus.size()); }
 };
 
-// Modelled shared-memory accesses per NEW element of one box array in the strip kernel:
-// x[i] and x[i - m d] loads plus the D store.
-constexpr double kPassCost = 3.0;
-
 // bit[w - lo] = 1 for taps, lo <= 0 <= hi.  Exact cover of every residue class of stride d by
 // boxes of the given lengths plus +/- single taps, minimising loads (dynamic programme).
 bool cover(const std::vector<uint8_t>& bit, int lo, int hi, int d, int nk, const int* m,
@@ -94,7 +90,7 @@ bool cover(const std::vector<uint8_t>& bit, int lo, int hi, int d, int nk, const
     p.nk = 1;
   }
   if (p.box[0].empty()) return false;
-  p.cost = double(p.n_terms()) + kPassCost * p.nk;
+  p.cost = double(p.n_terms());
   *out = p;
   return true;
 }
@@ -117,7 +113,11 @@ bool exact(const CombPlan& p, const std::vector<uint8_t>& bit, int lo, int hi) {
   return true;
 }
 
-bool best_comb(const int32_t* taps, int n, CombPlan* best) {
+// Searches comb decompositions over strides d_lo..d_hi under the cost model of the run-time
+// specialised kernel (filter_comb_e.cuh): loads per output = number of terms, whatever the
+// number of box lengths, and the two box lengths together must fit the register rings
+// (max_ring values per chain).
+bool best_comb(const int32_t* taps, int n, int d_lo, int d_hi, int max_ring, CombPlan* best) {
   const int lo = std::min(taps[0], 0), hi = std::max(taps[n - 1], 0);
   const int64_t span = int64_t(hi) - lo + 1;
   if (n < 8 || span > (1 << 20)) return false;
@@ -126,8 +126,9 @@ bool best_comb(const int32_t* taps, int n, CombPlan* best) {
   // candidate strides: fewest maximal progressions
   int64_t d_max = std::min<int64_t>(span - 1, 8192);
   d_max = std::min<int64_t>(d_max, std::max<int64_t>(64, 40000000 / n));
+  d_max = std::min<int64_t>(d_max, d_hi);
   std::vector<std::pair<int, int>> ranked;  // (progressions, d)
-  for (int d = 1; d <= d_max; ++d) {
+  for (int d = d_lo; d <= d_max; ++d) {
     int chains = 0;
     for (int i = 0; i < n; ++i) {
       const int64_t prev = int64_t(taps[i]) - d;
@@ -137,7 +138,7 @@ bool best_comb(const int32_t* taps, int n, CombPlan* best) {
   }
   std::sort(ranked.begin(), ranked.end());
   bool found = false;
-  const int n_strides = std::min<int>(6, int(ranked.size()));
+  const int n_strides = std::min<int>(12, int(ranked.size()));
   for (int r = 0; r < n_strides; ++r) {
     const int d = ranked[r].second;
     // progression lengths, with and without bridging the (absent) centre tap
@@ -162,13 +163,16 @@ bool best_comb(const int32_t* taps, int n, CombPlan* best) {
       }
     }
     std::sort(lengths.rbegin(), lengths.rend());
-    const int n_len = std::min<int>(4, int(lengths.size()));
+    const int n_len = std::min<int>(6, int(lengths.size()));
     for (int i = 0; i < n_len; ++i) {
       for (int j = i; j < n_len; ++j) {
         int m[2] = {lengths[i].second, lengths[j].second};
         CombPlan p;
         if (!cover(bit, lo, hi, d, i == j ? 1 : 2, m, &p)) continue;
         if (p.n_terms() > kMaxTerms) continue;
+        const int ring = p.m[0] + (p.nk > 1 ? p.m[1] : 0);
+        if (ring > max_ring) continue;
+        p.cost = double(p.n_terms()) + 1e-3 * ring;  // fewer loads, then fewer registers
         if (p.cost < best->cost) {
           *best = p;
           found = true;
@@ -257,7 +261,8 @@ int parrm_filter_plan(const int32_t* h_taps, int32_t n_taps, int dtype, int stra
   if (strategy == PARRM_PLAN_GATHER) return PARRM_OK;
 
   CombPlan best;
-  const bool ok = best_comb(h_taps, n_taps, &best);
+  const bool ok = best_comb(h_taps, n_taps, kPatternFirstMinStride, kPatternFirstMaxStride,
+                            kPatternFirstMaxRing, &best);
   const bool worth = ok && (strategy == PARRM_PLAN_COMB || best.cost < 0.6 * double(n_taps));
   if (!worth) {
     if (strategy == PARRM_PLAN_COMB) {

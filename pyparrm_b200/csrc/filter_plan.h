@@ -10,22 +10,24 @@
 // with "comb boxes"  D_k[i] = sum_{q=0}^{m_k - 1} x[i - q*d]  of at most two window lengths
 // m_0, m_1 over one common stride d.  The taps of a phase-matched comb sit near the multiples
 // of the period, so for d ~ an integer multiple of the period they fall into a few long
-// arithmetic progressions; a progression of m_k members costs one shared-memory load from the
-// D_k array instead of m_k loads from x.  The identity is over integers (which offsets are
-// summed), so the result differs from the plain gather only by floating-point association.
+// arithmetic progressions.  The kernel sums over the boxes first (a short "pattern"
+// E_k[i] = sum_b x[i - a_kb], one shared-memory load per box) and runs the comb as a sliding
+// sum of E_k along the chain t, t + d, t + 2d, ... in registers.  The identity is over
+// integers (which offsets are summed), so the result differs from the plain gather only by
+// floating-point association.
 #pragma once
 #include <stdint.h>
 
 namespace parrm {
 
 constexpr uint32_t kPlanMagic = 0x4D525250u;  // "PRRM"
-constexpr uint32_t kPlanVersion = 3;
+constexpr uint32_t kPlanVersion = 4;
 constexpr int kMaxTerms = 120;                // structured terms passed as kernel parameters
 constexpr int kMaxBoxKinds = 2;
 
 enum PlanKind : int32_t {
   kPlanGather = 0,  // one shared-memory load per tap
-  kPlanComb = 1     // comb boxes + single taps (see above)
+  kPlanComb = 1     // comb boxes + single taps (see above); taps are kept for the gather
 };
 
 struct FilterPlanHeader {
@@ -57,5 +59,12 @@ struct FilterPlanHeader {
   int32_t reserved[6];
 };
 static_assert(sizeof(FilterPlanHeader) == 128, "plan header is 128 bytes");
+
+// The decomposition is chosen for the run-time specialised kernel (filter_comb_e.cuh): one
+// thread per residue of the stride, so 64 <= d <= 992; every term is one shared-memory load
+// per output, so cost = number of terms; the box lengths are bounded by the register rings.
+constexpr int kPatternFirstMinStride = 64;
+constexpr int kPatternFirstMaxStride = 992;
+constexpr int kPatternFirstMaxRing = 60;   // M0 + M1
 
 }  // namespace parrm

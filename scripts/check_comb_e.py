@@ -20,6 +20,8 @@ CASES = {
     "cfg3": (1000 / 145 * (1 + 3e-6), None, 2469, 0, "both"),
     "cfg1": (1.3311148014466094, 0.01, 2000, 20, "both"),
     "cfg2past": (2000 / 130 * (1 + 3e-6), None, 2000, 0, "past"),
+    "cfg4": (30000 / 130 * (1 + 3e-6), None, 2311, 0, "past"),
+    "cfg4f": (30000 / 130 * (1 + 3e-6), None, 2311, 0, "future"),
 }
 
 
@@ -37,7 +39,7 @@ def parity():
             x = rng.standard_normal(shape) * 3 + 10
             want = oracle.apply_filter_direct(x, taps)
             d_x = torch.from_numpy(x).cuda()
-            for kern in (K.KERNEL_SPECIALISED, K.KERNEL_STRIP, K.KERNEL_GATHER):
+            for kern in (K.KERNEL_SPECIALISED, K.KERNEL_GATHER):
                 got = eng.filter_device(d_x, taps, kernel=kern).cpu().numpy()
                 err = np.abs(got - want).max() / np.abs(x).max()
                 worst = max(worst, err)
@@ -76,10 +78,14 @@ def timing(name="cfg2", n_chans=64, n_samples=1_200_000, tunings=({},)):
     d_x = torch.randn((n_chans, n_samples), dtype=torch.float64, device="cuda", generator=g)
     d_out = torch.empty_like(d_x)
     rows = []
-    for kern, tuning in [(K.KERNEL_STRIP, {})] + [(K.KERNEL_SPECIALISED, t) for t in tunings]:
-        for _ in range(3):
-            eng.filter_device(d_x, taps, d_out=d_out, kernel=kern, tuning=tuning)
-        torch.cuda.synchronize()
+    for kern, tuning in [(K.KERNEL_GATHER, {})] + [(K.KERNEL_SPECIALISED, t) for t in tunings]:
+        try:
+            for _ in range(3):
+                eng.filter_device(d_x, taps, d_out=d_out, kernel=kern, tuning=tuning)
+            torch.cuda.synchronize()
+        except RuntimeError as err:
+            print(json.dumps(dict(case=name, tuning=tuning, error=str(err)[:120])))
+            continue
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n = 20
         e0.record()
@@ -99,11 +105,15 @@ if __name__ == "__main__":
     t0 = time.time()
     if "--no-parity" not in sys.argv:
         print("worst", parity())
-    tunings = [{}, {"steps_per_chunk": 4}, {"steps_per_chunk": 10}, {"steps_per_chunk": 3},
-               {"prefetch_chunks": 6}, {"prefetch_chunks": 2}, {"ctas_per_sm": 1},
-               {"steps_per_chunk": 4, "ctas_per_sm": 1}]
-    rows = timing("cfg2", 64, 1_200_000, tunings)
-    rows += timing("cfg3", 64, 1_200_000, [{}])
+    def grid(us, pfs=(2, 4), ctas=(1, 2)):
+        return [{}] + [{"steps_per_chunk": u, "prefetch_chunks": pf, "ctas_per_sm": c}
+                       for u in us for pf in pfs for c in ctas]
+
+    rows = timing("cfg2", 64, 1_200_000, grid((5, 10), (2,), (2,)))
+    rows += timing("cfg3", 64, 1_200_000, grid((5, 7, 9, 13), (2, 4)))
+    rows += timing("cfg4", 64, 1_200_000, grid((4, 8, 10), (2,)))
+    rows += timing("cfg4f", 64, 1_200_000, grid((8,), (2,), (2,)))
+    rows += timing("cfg1", 64, 1_200_000, grid((1, 2, 3), (2, 4), (1,)))
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/check_comb_e.jsonl", "w") as f:
         for r in rows:

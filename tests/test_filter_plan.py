@@ -1,4 +1,4 @@
-"""Filter planner (host side of the C ABI) and the strip-kernel design, on the CPU.
+"""Filter planner (host side of the C ABI) and the specialised kernel's design, on the CPU.
 
 The planner regroups the tap set of ``_generate_filter`` (parrm.py:803-833) into comb boxes
 plus single taps (pyparrm_b200/csrc/filter_plan.h).  That is only legal if it is an identity
@@ -10,7 +10,7 @@ import pytest
 
 from oracle import parrm_oracle as oracle
 from pyparrm_b200 import _native
-from tests.strip_model import StripModel
+from tests.pattern_model import PatternModel
 
 
 def expand(desc, lo, hi):
@@ -72,6 +72,12 @@ def test_baseline_configs_get_short_plans():
     _, desc = _native.plan_filter(taps)
     assert desc["kind"] == 1 and desc["stride"] == 200 and sorted(desc["windows"]) == [10, 20]
     assert sum(len(b) for b in desc["boxes"]) + len(desc["plus"]) + len(desc["minus"]) <= 12
+    # the other named tap sets: cfg3 198 taps, cfg4 95 one-sided taps
+    for fs, fa, hw, direction, most in ((1000, 145, 2469, "both", 10), (30000, 130, 2311, "past", 16)):
+        period = fs / fa * (1 + 3e-6)
+        _, desc = _native.plan_filter(oracle.tap_offsets(period, period / 50, hw, 0, direction))
+        n_terms = sum(len(b) for b in desc["boxes"]) + len(desc["plus"]) + len(desc["minus"])
+        assert desc["kind"] == 1 and 64 <= desc["stride"] <= 992 and n_terms <= most
 
 
 def test_random_tap_sets():
@@ -95,35 +101,32 @@ def test_random_tap_sets():
 
 
 MODEL_CASES = [
-    # case index, recording length, tile, prefetch, gamma, pieces, reinit, time chunk
-    (0, 30_011, 512, 3, 1, 3, 0, None),
-    (0, 700, 512, 3, 0, 1, 0, None),
-    (0, 20_000, 256, 4, 0, 2, 5, None),
-    (0, 40_000, 1024, 2, 1, 2, 0, (9_000, 21_000)),
-    (2, 20_000, 512, 3, 0, 2, 0, None),
-    (3, 20_000, 1024, 2, 1, 1, 7, None),
-    (4, 19_130, 512, 3, 0, 1, 0, None),
-    (5, 19_130, 512, 3, 0, 4, 0, None),
-    (12, 15_000, 256, 2, 0, 3, 0, (0, 7_000)),
+    # case index, recording length, steps per chunk, gamma, pieces, time chunk
+    (0, 30_011, 5, 1, 3, None),
+    (0, 700, 10, 0, 1, None),
+    (0, 20_000, 3, 0, 2, None),          # block longer than the box (B = 21 > M0 = 20)
+    (0, 40_000, 10, 1, 2, (9_000, 21_000)),
+    (1, 30_000, 7, 0, 2, None),          # cfg3: M0 = 25, B = 28
+    (2, 20_000, 8, 0, 2, None),          # cfg4, documented "past"
+    (3, 20_000, 8, 1, 1, None),
+    (4, 19_130, 3, 0, 1, None),
+    (12, 15_000, 4, 0, 3, (0, 7_000)),
 ]
 
 
-@pytest.mark.parametrize("pipe", [0, 2, 3])
 @pytest.mark.parametrize("spec", MODEL_CASES)
-def test_strip_design_matches_oracle(spec, pipe):
-    """Ring slots, mirror chunk, sliding boxes, piece boundaries and edge counts of the strip
-    kernels (NumPy model with their index arithmetic) against the oracle's direct sum.
-    ``pipe`` = number of hand-over stages of the producer/consumer kernel (0: two-phase kernel);
-    the model runs the slide the full ``stages - 1`` chunks ahead of the gather."""
-    case, n_total, tile, prefetch, gamma, pieces, reinit, chunk = spec
+def test_pattern_first_design_matches_oracle(spec):
+    """Chunk grid, priming block, register rings of the unrolled block, sliding sums, piece
+    boundaries and edge counts of the run-time specialised kernel (NumPy model with its index
+    arithmetic, tests/pattern_model.py) against the oracle's direct sum."""
+    case, n_total, u, gamma, pieces, chunk = spec
     period, phw, hw, omit, direction = CASES[case]
     taps = oracle.tap_offsets(period, period / 50 if phw is None else phw, hw, omit, direction)
     _, desc = _native.plan_filter(taps, strategy=_native.PLAN_COMB)
     rng = np.random.default_rng(case)
     x = rng.standard_normal((1, n_total)) + 3.0
     want = oracle.apply_filter_direct(x, taps)[0]
-    model = StripModel(taps, desc, tile, prefetch, 0 if pipe else reinit, pipe=bool(pipe),
-                       stages=max(pipe, 2))
+    model = PatternModel(taps, desc, u)
     if chunk is None:
         got = model.run(x[0], 0, 0, n_total, n_total, gamma, pieces)
     else:
@@ -133,3 +136,24 @@ def test_strip_design_matches_oracle(spec, pipe):
         want = want[t0:t1]
     assert not np.isnan(got).any()
     assert np.abs(got - want).max() <= 1e-12
+
+
+def test_pattern_first_non_finite_window():
+    """A NaN / Inf sample zeroes exactly the outputs whose tap window (or own sample) holds
+    it -- parrm.py:869's isfinite -> 0 applied per output -- and outputs past the window are
+    exact again (the running sums are re-added from the rings while they are non-finite)."""
+    period, phw, hw, omit, direction = CASES[0]
+    taps = oracle.tap_offsets(period, period / 50, hw, omit, direction)
+    _, desc = _native.plan_filter(taps, strategy=_native.PLAN_COMB)
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((1, 40_000))
+    x[0, 12_345] = np.nan
+    x[0, 30_000] = np.inf
+    x[0, 5] = 1e12
+    with np.errstate(invalid="ignore"):
+        want = oracle.apply_filter_direct(x, taps)[0]
+    want[~np.isfinite(want)] = 0.0
+    got = PatternModel(taps, desc, 10).run(x[0], 0, 0, 40_000, 40_000, 0, 2)
+    assert np.isfinite(got).all()
+    assert np.array_equal(got == 0, want == 0)
+    assert np.abs(got - want).max() <= 1e-3  # 1e12 outlier: rounding residue ~1e12 * 2^-52 * steps
