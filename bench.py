@@ -12,19 +12,28 @@ one pass of the filter over the whole recording.
   array in and a host array out: H2D + kernel + D2H inside the timed region every step.
 * ``roofline`` -- 16 algorithmic bytes per channel-sample (8 read + 8 written) / kernel time,
   against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
-* ``cpu_baseline`` -- the reference's arithmetic for this path (two SciPy FFT convolutions,
-  oracle port) on a bounded sample of the same recording, on this host.
+* ``cpu_baseline`` -- the UNMODIFIED reference (``oracle/_ref``, a verbatim copy made by
+  ``oracle/vendor_ref.py``, imported through the dispatch-only shims of ``oracle/ref_shim.py``)
+  running ``PARRM.filter_data()`` on all 64 channels of the same recording, on this host.
 * ``find_period`` -- second metric of BASELINE.json: candidate periods/s of the evaluator on
   the same recording (run-3 shape: ~24.7 k random samples x 64 channels, 20 harmonics, the
-  388-candidate grid), with its FP64-pipe roofline and CPU baseline.
+  388-candidate grid), with its FP64-pipe roofline and the reference's ``_optimise_local`` on
+  all host threads beside it (plus a labelled non-reference process-parallel line).
+* ``e2e_variants`` -- the same API call with a pageable array, with the caller's array
+  registered in place, and with float32 in / float32 out (half the PCIe bytes).
+* ``cfg1`` -- BASELINE configs[0]: find_period + create_filter + filter_data on the bundled
+  example recording, wall time here and for the reference on this host.
+* ``strong`` -- strong-scaling cases: cfg4 (384 channels x 9 M samples, one-sided filter,
+  channel-sharded) and a cfg5 candidate sweep (1e5 periods, winner by one (error, index)
+  pair per rank).
 
-``--impl reference`` times the reference's CPU implementation (oracle port; the reference is
-pure Python and cannot be pip-installed here: its build backend ``hatchling`` is absent) on
-bounded samples of the same workload; rank 0 only.
+``--impl reference`` times the unmodified reference's ``PARRM.filter_data()`` on this host's
+cores on bounded samples of the same workload; rank 0 only; it maps no library of this repo.
 
-Multi-GPU (torchrun, one rank per GPU): weak scaling.  Filtering shards by channel with no
-collective -- every rank filters its own 64-channel recording; the period search shards the
-candidate grid and all-gathers the errors over NCCL.
+Multi-GPU (torchrun, one rank per GPU) goes through the product's own sharding API:
+``pyparrm_b200.enable_sharding()`` + ``PARRM.filter_data()`` / ``PARRM.find_period()``.  Weak
+scaling for the headline: the recording grows to N x 64 channels, channel-sharded, no
+collective; the period search shards the candidate grid and all-gathers the errors over NCCL.
 """
 
 from __future__ import annotations
@@ -158,63 +167,131 @@ def barrier(dist):
 
 
 # ----------------------------------------------------------------------------- CPU legs
-def cpu_filter_pass(oracle, sample: np.ndarray, filt: np.ndarray) -> float:
-    t0 = time.perf_counter()
-    oracle.apply_filter_fft(sample, filt)
-    return time.perf_counter() - t0
+def import_reference():
+    """The unmodified reference package (oracle/_ref or /root/reference), or None."""
+    from oracle import ref_shim
+
+    if not ref_shim.reference_available():
+        return None, "reference neither mounted nor vendored (python oracle/vendor_ref.py)"
+    return ref_shim.import_reference(), ref_shim.reference_location()
 
 
-def cpu_filter_baseline(data, filt, n_sample_chans=32):
-    from oracle import parrm_oracle as oracle
+def reference_filter_object(pyparrm, data, period):
+    """Reference PARRM object with the benchmark's filter, period injected (the filter
+    benchmark does not depend on the search)."""
+    ref = pyparrm.PARRM(data, FS, FA, verbose=False)
+    ref._period = np.float64(period)
+    ref.create_filter(filter_half_width=HALF_WIDTH, filter_direction="both")
+    return ref
 
-    sample = data[:n_sample_chans]
-    seconds = cpu_filter_pass(oracle, sample, filt)
+
+def cpu_filter_baseline(data, period):
+    """Reference filter_data() on the whole recording, one pass (single-threaded by design:
+    scipy.signal.convolve, parrm.py:861-866)."""
+    pyparrm, where = import_reference()
+    if pyparrm is None:
+        from oracle import parrm_oracle as oracle
+
+        filt = oracle.build_filter(period, period / 50, HALF_WIDTH, 0, "both")
+        t0 = time.perf_counter()
+        oracle.apply_filter_fft(data, filt)
+        seconds = time.perf_counter() - t0
+        kind, what = "port", f"oracle port ({where})"
+    else:
+        ref = reference_filter_object(pyparrm, data, period)
+        t0 = time.perf_counter()
+        ref.filter_data()
+        seconds = time.perf_counter() - t0
+        kind, what = "reference", f"unmodified reference PARRM.filter_data() from {where}"
     return {
-        "value": sample.size / seconds, "unit": "channel-samples/s", "cores": 1, "kind": "port",
-        "sample": f"{n_sample_chans} of {data.shape[0]} channels x {data.shape[1]} samples, 1 pass, "
-                  f"{seconds:.1f} s; scipy.signal.convolve (FFT) twice as parrm.py:861-866, "
-                  "single-threaded as in the reference",
+        "value": data.size / seconds, "unit": "channel-samples/s", "cores": 1, "kind": kind,
+        "sample": f"all {data.shape[0]} channels x {data.shape[1]} samples, 1 pass, {seconds:.1f} s; "
+                  f"{what}; single-threaded as the reference runs it",
     }
 
 
 def cpu_search_baseline(data, indices, periods, bandwidth, n_candidates=None):
+    """Reference _optimise_local over grid candidates on all host threads (the pqdm.threads map
+    of parrm.py:445-454), plus a labelled NON-reference process-parallel line (joblib)."""
     from oracle import parrm_oracle as oracle
 
     cores = os.cpu_count() or 1
-    n_candidates = n_candidates or max(cores, 8)
+    n_candidates = n_candidates or max(cores, 16)
     z = oracle.standardise(data, 3.0)
     pick = periods[np.linspace(0, len(periods) - 1, n_candidates).astype(int)]
-    t0 = time.perf_counter()
-    oracle.objective_many(pick, z, indices, bandwidth, 1.0, data.shape[0], n_jobs=cores)
-    seconds = time.perf_counter() - t0
-    return {
-        "value": n_candidates / seconds, "unit": "candidates/s", "cores": cores, "kind": "port",
+    pyparrm, where = import_reference()
+    if pyparrm is not None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        ref = pyparrm.PARRM(data, FS, FA, verbose=False)
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=cores) as pool:
+            list(pool.map(lambda p: ref._optimise_local(p, z, indices, bandwidth, 1.0), pick))
+        seconds = time.perf_counter() - t0
+        kind, what = "reference", f"unmodified reference PARRM._optimise_local from {where}"
+    else:
+        t0 = time.perf_counter()
+        oracle.objective_many(pick, z, indices, bandwidth, 1.0, data.shape[0], n_jobs=cores)
+        seconds = time.perf_counter() - t0
+        kind, what = "port", "oracle port"
+    line = {
+        "value": n_candidates / seconds, "unit": "candidates/s", "cores": cores, "kind": kind,
         "sample": f"{n_candidates} of {len(periods)} grid candidates x {len(indices)} samples x "
                   f"{data.shape[0]} channels, bw={bandwidth}, {cores} threads (pqdm.threads "
-                  f"equivalent), {seconds:.1f} s",
+                  f"equivalent), {seconds:.1f} s; {what}",
     }
+    try:  # best-effort CPU line, NOT the reference's execution model (SURVEY 8(d))
+        from joblib import Parallel, delayed
+
+        workers = min(cores, n_candidates)
+        t0 = time.perf_counter()
+        Parallel(n_jobs=workers)(delayed(oracle.objective)(p, z, indices, bandwidth, 1.0,
+                                                           data.shape[0]) for p in pick)
+        seconds = time.perf_counter() - t0
+        line["non_reference_process_parallel"] = {
+            "value": n_candidates / seconds, "unit": "candidates/s", "cores": workers,
+            "what": f"joblib processes over candidates, oracle port of the objective, {seconds:.1f} s "
+                    "(includes shipping the standardised recording to the workers)"}
+    except Exception as err:  # noqa: BLE001
+        line["non_reference_process_parallel"] = {"unavailable": str(err)[:100]}
+    return line
 
 
 # ----------------------------------------------------------------------------- reference arm
 def run_reference(args):
+    """Times the unmodified reference.  Imports nothing that maps libparrm_b200.so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import parrm_oracle as oracle
-    from pyparrm_b200.synthetic import make_recording, true_period
+    from pyparrm_b200.synthetic import make_recording, true_period  # pure NumPy module
 
     period = true_period(FS, FA)
-    filt = oracle.build_filter(period, period / 50, HALF_WIDTH, 0, "both")
+    pyparrm, where = import_reference()
     probe = make_recording(2, N_SAMPLES, FS, FA, seed=0)
-    per_chan = cpu_filter_pass(oracle, probe, filt) / 2
-    budget = 150.0
+    if pyparrm is not None:
+        run_pass = lambda obj: obj.filter_data()  # noqa: E731
+        make = lambda d: reference_filter_object(pyparrm, d, period)  # noqa: E731
+        kind = "reference"
+        what = f"unmodified reference PARRM.filter_data() (parrm.py:835-875) from {where}"
+    else:
+        from oracle import parrm_oracle as oracle
+
+        filt = oracle.build_filter(period, period / 50, HALF_WIDTH, 0, "both")
+        run_pass = lambda d: oracle.apply_filter_fft(d, filt)  # noqa: E731
+        make = lambda d: d  # noqa: E731
+        kind, what = "port", f"oracle port of parrm.py:861-869 ({where})"
+    t0 = time.perf_counter()
+    run_pass(make(probe))
+    per_chan = (time.perf_counter() - t0) / 2
+    budget = 170.0
     n_chans = int(max(1, min(N_CHANS, budget / ((args.steps + args.warmup) * per_chan))))
     sample = make_recording(n_chans, N_SAMPLES, FS, FA, seed=0)
+    obj = make(sample)
     for _ in range(args.warmup):
-        cpu_filter_pass(oracle, sample, filt)
+        run_pass(obj)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle.apply_filter_fft(sample, filt)
+        run_pass(obj)
     seconds = time.perf_counter() - t0
     value = sample.size * args.steps / seconds
     line = {
@@ -223,12 +300,14 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * seconds / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "timing": "host wall clock (CPU path)"},
+        "config": {"workload": WORKLOAD, "taps": 160, "sharding": "CPU, rank 0 only",
+                   "l2": "n/a (CPU)", "timing": "host wall clock (CPU path)"},
         "cpu_baseline": {
-            "value": value, "unit": "channel-samples/s", "cores": 1, "kind": "port",
-            "sample": f"{n_chans} of {N_CHANS} channels x {N_SAMPLES} samples per step; oracle port "
-                      "of parrm.py:861-869 (scipy.signal.convolve, FFT, single-threaded as the "
-                      "reference runs it); reference not pip-installable here (hatchling absent)",
+            "value": value, "unit": "channel-samples/s", "cores": 1, "kind": kind,
+            "sample": f"{n_chans} of {N_CHANS} channels x {N_SAMPLES} samples per step (as many "
+                      f"channels as fit {budget:.0f} s for {args.steps}+{args.warmup} steps; the rate "
+                      f"per channel does not depend on the count); {what}; scipy.signal.convolve "
+                      "(FFT), single-threaded as the reference runs it",
         },
         "e2e": {"value": value, "unit": "channel-samples/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -238,26 +317,53 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- B200 arm
+def timed_api_passes(dist, fn, steps):
+    import torch
+
+    barrier(dist)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = fn()
+    torch.cuda.synchronize()
+    seconds = max_over_ranks(dist, time.perf_counter() - t0)
+    barrier(dist)
+    return seconds, out
+
+
 def run_b200(args):
     import torch
 
-    from oracle import parrm_oracle as oracle  # cpu_baseline leg only
-    from pyparrm_b200 import PARRM, _engine, _native, pinned_empty
+    from oracle import parrm_oracle as oracle  # cpu legs and the parity guard only
+    from pyparrm_b200 import (PARRM, _engine, _sharding, disable_sharding, enable_sharding,
+                              pin_array, pinned_empty)
     from pyparrm_b200.synthetic import make_recording, true_period
 
     dist, world, rank, local = dist_setup(args.gpus)
     engine = _engine.get_engine()
     hbm_peak, peak_source = measured_peaks()
-
-    # this rank's recording (weak scaling: every GPU gets a full cfg2 recording)
-    data = pinned_empty((N_CHANS, N_SAMPLES))
-    make_recording(N_CHANS, N_SAMPLES, FS, FA, seed=rank, out=data)
     period = true_period(FS, FA)
-    parrm = PARRM(data, FS, FA, verbose=False)
-    parrm._period = np.float64(period)  # the filter benchmark does not depend on the search
+    units = N_CHANS * N_SAMPLES
+
+    # The job: one recording of world x 64 channels (weak scaling), channel-sharded by the
+    # product's own plan.  Every rank materialises only its rows of the host array (the other
+    # rows are never touched: PARRM holds `data` by reference and a rank reads its shard only).
+    total_chans = world * N_CHANS
+    if world > 1:
+        enable_sharding(gather="none")
+        recording = np.empty((total_chans, N_SAMPLES), dtype=np.float64)
+    else:
+        recording = pinned_empty((total_chans, N_SAMPLES))
+    parrm = PARRM(recording, FS, FA, verbose=False)
+    parrm._period = np.float64(period)
     parrm.create_filter(filter_half_width=HALF_WIDTH, filter_direction="both")
     taps = (np.flatnonzero(parrm.filter < 0) - HALF_WIDTH).astype(np.int32)
-    units = N_CHANS * N_SAMPLES
+    w_lo, w_hi = min(int(taps[0]), 0), max(int(taps[-1]), 0)
+    c0, c1, t0_, t1_, _, _ = _sharding.channel_or_time_shards(total_chans, N_SAMPLES, world,
+                                                              w_lo, w_hi)[rank]
+    assert (c1 - c0, t0_, t1_) == (N_CHANS, 0, N_SAMPLES)
+    data = recording[c0:c1]
+    make_recording(N_CHANS, N_SAMPLES, FS, FA, seed=rank, out=data)
+    pin = pin_array(data) if world > 1 else None  # in place: only this rank's rows are locked
 
     d_x = torch.from_numpy(data).cuda()
     d_y = torch.empty_like(d_x)
@@ -276,36 +382,42 @@ def run_b200(args):
         stop.record(stream)
         barrier(dist)
         launches = engine.launches - launches0
+        filter_kernel = engine.last_filter_kernel
         dev_seconds = max_over_ranks(dist, start.elapsed_time(stop) * 1e-3)
         kernel_seconds = start.elapsed_time(stop) * 1e-3 / args.steps  # one launch per step
 
-        # ---- e2e: public API, host in / host out -----------------------------------
+        # ---- e2e: public API, host in / host out (sharded through enable_sharding) ---
         for _ in range(min(args.warmup, 3)):
             parrm.filter_data()
         e2e_steps = max(3, min(args.steps, 20))
-        barrier(dist)
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            out = parrm.filter_data()
-        torch.cuda.synchronize()
-        e2e_seconds = max_over_ranks(dist, time.perf_counter() - t0)
-        barrier(dist)
+        e2e_seconds, out = timed_api_passes(dist, parrm.filter_data, e2e_steps)
+        assert tuple(parrm.filter_shard) == (c0, c1, 0, N_SAMPLES)
 
-        # ---- find_period evaluator (second metric) ---------------------------------
-        search = bench_search(engine, dist, world, rank, data, args)
+        # ---- find_period evaluator (second metric) + the sharded search API ----------
+        search = bench_search(engine, dist, world, rank, args)
+
+        # ---- strong-scaling cases (device resident) --------------------------------
+        strong = bench_strong(engine, dist, world, rank)
 
     # parity guard on what was just timed (3 channels against the oracle's direct form)
     want = oracle.apply_filter_direct(data[:3], taps)
     parity = float(np.abs(out[:3] - want).max() / np.abs(data[:3]).max())
     assert parity <= 1e-9, f"bench parity check failed: {parity:.3e}"
+    dev_parity = float(np.abs(d_y[:3].cpu().numpy() - want).max() / np.abs(data[:3]).max())
+    assert dev_parity <= 1e-9, f"bench parity check (device path) failed: {dev_parity:.3e}"
 
+    variants, cfg1 = {}, None
+    if world == 1:
+        variants = bench_e2e_variants(engine, data, taps, e2e_steps, period)
+        cfg1 = bench_cfg1(engine)
+    if pin is not None:
+        pin.release()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    filt = oracle.build_filter(period, period / 50, HALF_WIDTH, 0, "both")
-    cpu = cpu_filter_baseline(data, filt)
+    cpu = cpu_filter_baseline(data, period) if world == 1 else None
     achieved = BYTES_PER_CHANNEL_SAMPLE * units / kernel_seconds / 1e9
     traffic = None
     try:
@@ -323,7 +435,9 @@ def run_b200(args):
         "dtype": "f64", "data": "synthetic",
         "config": {
             "workload": WORKLOAD, "taps": int(taps.shape[0]),
-            "sharding": "one 64-channel recording per GPU, no collective" if world > 1 else "single GPU",
+            "sharding": (f"pyparrm_b200.enable_sharding(gather='none') + PARRM.filter_data() on one "
+                         f"[{total_chans} x {N_SAMPLES}] recording: channel shards of 64 per GPU, "
+                         "no collective" if world > 1 else "single GPU"),
             "l2": "inputs (614 MB/GPU) larger than L2 (126 MB); no flush needed",
             "timing": "CUDA events on the launching stream, max over ranks",
         },
@@ -332,30 +446,230 @@ def run_b200(args):
             "value": world * units * e2e_steps / e2e_seconds, "unit": "channel-samples/s",
             "h2d_bytes_per_step": units * 8, "d2h_bytes_per_step": units * 8,
             "steps": e2e_steps, "ms_per_step": 1e3 * e2e_seconds / e2e_steps,
-            "api": "PARRM.filter_data() on a pinned NumPy array, NumPy result",
+            "api": ("PARRM.filter_data() under enable_sharding(gather='none'); this rank's rows "
+                    "page-locked in place with pin_array()" if world > 1 else
+                    "PARRM.filter_data() on a pinned NumPy array, NumPy result"),
         },
         "gpu_launches": launches,
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
             "frac": achieved / hbm_peak, "traffic": traffic,
-            "kernel": "parrm_filter_apply", "peak_source": peak_source,
+            "kernel": filter_kernel, "peak_source": peak_source,
             "algorithmic_bytes_per_launch": BYTES_PER_CHANNEL_SAMPLE * units,
         },
-        "cpu_baseline": cpu,
-        "parity_max_rel_err": parity,
+        "parity_max_rel_err": max(parity, dev_parity),
         "find_period": search,
+        "strong": strong,
     }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    if variants:
+        line["e2e_variants"] = variants
+    if cfg1 is not None:
+        line["cfg1"] = cfg1
     print(json.dumps(line), flush=True)
     if dist is not None:
+        disable_sharding()
         dist.destroy_process_group()
 
 
-def bench_search(engine, dist, world, rank, data, args):
-    """Evaluator throughput on the run-3 shape of this recording; candidates sharded over ranks."""
+def bench_e2e_variants(engine, data, taps, steps, period):
+    """The API call as existing callers make it (pageable np.ndarray), with the caller's array
+    registered in place, and with half the PCIe bytes (float32 in, float32 out)."""
     import torch
 
-    from pyparrm_b200 import _native
+    from pyparrm_b200 import PARRM, pin_array
 
+    def rate(array, **kw):
+        p = PARRM(array, FS, FA, verbose=False)
+        p._period = np.float64(period)
+        p.create_filter(filter_half_width=HALF_WIDTH, filter_direction="both")
+        for _ in range(2):
+            p.filter_data(**kw)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            p.filter_data(**kw)
+        torch.cuda.synchronize()
+        seconds = time.perf_counter() - t0
+        return {"value": array.size * steps / seconds, "unit": "channel-samples/s",
+                "ms_per_step": 1e3 * seconds / steps}
+
+    out = {}
+    pageable = np.array(data)  # ordinary malloc'ed copy, as np.load would hand over
+    out["pageable_f64"] = dict(rate(pageable), h2d_bytes_per_step=data.size * 8,
+                               d2h_bytes_per_step=data.size * 8,
+                               what="pageable float64 in (staged through pinned buffers by "
+                                    "8 copy threads), float64 out")
+    t0 = time.perf_counter()
+    handle = pin_array(pageable)
+    register_ms = 1e3 * (time.perf_counter() - t0)
+    out["registered_f64"] = dict(rate(pageable), register_ms=register_ms,
+                                 what="same array after pyparrm_b200.pin_array(data) "
+                                      "(cudaHostRegister once, direct copies afterwards)")
+    handle.release()
+    x32 = pageable.astype(np.float32)
+    h32 = pin_array(x32)
+    out["f32_in_f32_out"] = dict(rate(x32, out_dtype=np.float32), h2d_bytes_per_step=data.size * 4,
+                                 d2h_bytes_per_step=data.size * 4,
+                                 what="float32 recording uploaded as float32, widened on the device, "
+                                      "float64 arithmetic, filter_data(out_dtype=float32)")
+    h32.release()
+    return out
+
+
+def bench_cfg1(engine):
+    """BASELINE configs[0]: the bundled example recording, whole workflow."""
+    import torch
+
+    from pyparrm_b200 import PARRM, get_example_data_paths
+
+    data = np.load(get_example_data_paths("example_data"))
+
+    def workflow(cls):
+        p = cls(data, 200, 150, verbose=False)
+        p.find_period()
+        p.create_filter(filter_half_width=2000, omit_n_samples=20, filter_direction="both",
+                        period_half_width=0.01)
+        return p, p.filter_data()
+
+    workflow(PARRM)  # builds / loads kernels
+    torch.cuda.synchronize()
+    launches0 = engine.launches
+    t0 = time.perf_counter()
+    p, out = workflow(PARRM)
+    torch.cuda.synchronize()
+    gpu_seconds = time.perf_counter() - t0
+    result = {"workload": "cfg1: bundled example DBS recording (1 x 19130, 200 Hz / 150 Hz): "
+                          "find_period() + create_filter(2000, 20, 'both', 0.01) + filter_data()",
+              "gpu_seconds": gpu_seconds, "gpu_launches": engine.launches - launches0,
+              "period": float(p.period)}
+    pyparrm, where = import_reference()
+    if pyparrm is not None:
+        t0 = time.perf_counter()
+        ref, ref_out = workflow(pyparrm.PARRM)
+        result["reference_seconds"] = time.perf_counter() - t0
+        result["reference_period"] = float(ref.period)
+        result["period_equal"] = bool(ref.period == p.period)
+        result["filtered_max_abs_diff"] = float(np.abs(ref_out - out).max())
+        result["reference"] = f"unmodified reference from {where}, n_jobs=1 (its default)"
+    return result
+
+
+def bench_strong(engine, dist, world, rank):
+    """Strong scaling, device resident: total work fixed, split by the product's plan."""
+    import torch
+
+    from oracle import parrm_oracle as oracle  # tap list of the named filter only
+    from pyparrm_b200 import _sharding
+
+    out = {}
+    # ---- cfg4: 384 channels x 9 M samples (30 kHz x 300 s), one-sided filter ------------
+    n_chans, n_samples, fs, fa, hw = 384, 9_000_000, 30000, 130, 2311
+    per4 = fs / fa * (1 + 3e-6)
+    taps = oracle.tap_offsets(per4, per4 / 50, hw, 0, "past")
+    c0, c1, _, _, _, _ = _sharding.channel_or_time_shards(
+        n_chans, n_samples, world, min(int(taps[0]), 0), max(int(taps[-1]), 0))[rank]
+    gen = torch.Generator(device="cuda").manual_seed(100 + rank)
+    d_x = torch.randn((c1 - c0, n_samples), dtype=torch.float64, device="cuda", generator=gen)
+    d_y = torch.empty_like(d_x)
+    for _ in range(2):
+        engine.filter_device(d_x, taps, d_out=d_y)
+    barrier(dist)
+    steps = 5
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream = torch.cuda.current_stream()
+    start.record(stream)
+    for _ in range(steps):
+        engine.filter_device(d_x, taps, d_out=d_y)
+    stop.record(stream)
+    barrier(dist)
+    mine = start.elapsed_time(stop) * 1e-3
+    seconds = max_over_ranks(dist, mine)
+    hbm_peak, _ = measured_peaks()
+    # spot parity at full size: one channel's window against the oracle's direct sum
+    lo = 4_000_000
+    xs = d_x[0, lo - 3000: lo + 8000].cpu().numpy()[None, :]
+    ys = d_y[0, lo: lo + 5000].cpu().numpy()
+    ref = oracle.apply_filter_direct(xs, taps)[0, 3000:8000]
+    spot = float(np.abs(ys - ref).max() / np.abs(xs).max())
+    assert spot <= 1e-9, f"cfg4 spot parity {spot:.3e}"
+    out["cfg4_filter"] = {
+        "workload": "cfg4: 384 ch x 9.0 M samples f64 (27.6 GB), 130 Hz at 30 kHz, one-sided "
+                    f"('past') default-width filter, {len(taps)} taps; channel-sharded {c1 - c0} per GPU",
+        "value": n_chans * n_samples * steps / seconds, "unit": "channel-samples/s",
+        "ms_per_step": 1e3 * seconds / steps, "scaling": "strong",
+        "kernel": engine.last_filter_kernel,
+        "roofline_frac_this_rank": 16.0 * (c1 - c0) * n_samples * steps / mine / 1e9 / hbm_peak,
+        "spot_parity_rel_err": spot,
+    }
+    del d_x, d_y
+    # ---- cfg3 at full size on one GPU (256 ch x 3.6 M, 198 taps): roofline only ----------
+    if world == 1:
+        per3 = 1000 / 145 * (1 + 3e-6)
+        taps3 = oracle.tap_offsets(per3, per3 / 50, 2469, 0, "both")
+        d_x = torch.randn((256, 3_600_000), dtype=torch.float64, device="cuda", generator=gen)
+        d_y = torch.empty_like(d_x)
+        for _ in range(2):
+            engine.filter_device(d_x, taps3, d_out=d_y)
+        start.record(stream)
+        for _ in range(steps):
+            engine.filter_device(d_x, taps3, d_out=d_y)
+        stop.record(stream)
+        torch.cuda.synchronize()
+        sec3 = start.elapsed_time(stop) * 1e-3
+        out["cfg3_filter"] = {
+            "workload": f"cfg3: 256 ch x 3.6 M samples f64 (7.4 GB), 145 Hz at 1 kHz, default "
+                        f"half-width 2469, {len(taps3)} taps",
+            "value": 256 * 3_600_000 * steps / sec3, "unit": "channel-samples/s",
+            "ms_per_step": 1e3 * sec3 / steps, "kernel": engine.last_filter_kernel,
+            "roofline_frac": 16.0 * 256 * 3_600_000 * steps / sec3 / 1e9 / hbm_peak,
+        }
+        del d_x, d_y
+    # ---- cfg5: candidate sweep, winner only -------------------------------------------
+    n_cand, n_fit = 100_000, 100_000
+    rng = np.random.default_rng(7)
+    t = np.arange(n_fit + 1, dtype=np.float64)
+    p_true = FS / FA * (1 + 3e-6)
+    y = (np.sin(2 * np.pi * t / p_true) + 0.5 * rng.standard_normal(n_fit + 1))[None, :]
+    z = oracle.standardise(y, 3.0)
+    tile = engine.tile_from_standardised(z, np.arange(n_fit))
+    sweep = (FS / FA) * (1 + np.linspace(-1e-2, 1e-2, n_cand))
+    evaluate = lambda blk: engine.evaluate_device(tile, blk, 20, 1.0, 1)  # noqa: E731
+    if dist is not None:  # warm-up (workspace allocation, NCCL channel set-up)
+        _sharding.minloc_sharded(evaluate, sweep[:2048])
+    else:
+        evaluate(sweep[:2048])
+    barrier(dist)
+    t0 = time.perf_counter()
+    if dist is not None:
+        best, err = _sharding.minloc_sharded(evaluate, sweep)
+    else:
+        d_err = evaluate(sweep)
+        err, best = engine.argmin(d_err)
+    torch.cuda.synchronize()
+    seconds = max_over_ranks(dist, time.perf_counter() - t0)
+    out["cfg5_sweep"] = {
+        "workload": f"cfg5: {n_cand} candidate periods x {n_fit} contiguous samples x 1 channel, "
+                    "bandwidth 20, lambda 1; candidates in contiguous blocks per GPU, winner by one "
+                    "(error, index) pair per rank (_sharding.minloc_sharded)",
+        "value": n_cand / seconds, "unit": "candidates/s", "seconds": seconds, "scaling": "strong",
+        "winner_rel_err_vs_injected": abs(float(sweep[best]) - p_true) / p_true,
+        "winner_error": float(err),
+    }
+    return out
+
+
+def bench_search(engine, dist, world, rank, args):
+    """Evaluator throughput on the run-3 shape of the cfg2 recording (candidates sharded over
+    ranks by the product's evaluate_sharded), then the whole search through the public API."""
+    import torch
+
+    from pyparrm_b200 import PARRM, _native, _sharding
+    from pyparrm_b200.synthetic import make_recording, true_period
+
+    # the search needs the same recording on every rank (SPMD): the 64-channel cfg2 recording
+    data = make_recording(N_CHANS, N_SAMPLES, FS, FA, seed=0)
     n_chans, n_samples = data.shape
     rng = np.random.default_rng(0)
     lo, hi = int(np.floor(0.025 * n_samples)), int(n_samples - 2 - np.ceil(0.025 * n_samples))
@@ -365,24 +679,31 @@ def bench_search(engine, dist, world, rank, data, args):
     grid = np.unique(p0 * np.concatenate((1 + np.arange(-1e-2, 1e-2 + 1e-4, 1e-4) / 3,
                                           1 + np.arange(-1e-3, 1e-3 + 1e-5, 1e-5) / 3)))
     per_rank = 8 * len(grid)                                          # weak scaling: fixed per GPU
-    periods = np.resize(grid, per_rank) * (1 + 1e-9 * rank)
-    (tile,) = engine.prepare_tiles(data, [indices], 3.0)
-    d_periods = torch.from_numpy(periods).cuda()
+    periods = np.resize(grid, per_rank * world)
+    if world > 1:
+        (tile,) = _sharding.prepare_tiles_sharded(engine, data, [indices], 3.0)
+    else:
+        (tile,) = engine.prepare_tiles(data, [indices], 3.0)
     stream = torch.cuda.current_stream()
     steps = max(3, min(args.steps, 10))
+    evaluate = lambda blk: engine.evaluate_device(tile, blk, bandwidth, 1.0, n_chans)  # noqa: E731
+
+    def one_step():
+        if world > 1:  # block per rank + the one all-gather of the errors
+            return _sharding.evaluate_sharded(evaluate, periods)
+        return evaluate(periods).cpu().numpy()
+
     for _ in range(2):
-        d_err = engine.evaluate_device(tile, d_periods, bandwidth, 1.0, n_chans)
+        one_step()
     barrier(dist)
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record(stream)
     for _ in range(steps):
-        d_err = engine.evaluate_device(tile, d_periods, bandwidth, 1.0, n_chans)
-        if dist is not None:  # the one exchange step of the sharded search
-            gathered = torch.empty(world * per_rank, dtype=torch.float64, device="cuda")
-            dist.all_gather_into_tensor(gathered, d_err)
+        errors = one_step()
     stop.record(stream)
     barrier(dist)
     seconds = max_over_ranks(dist, start.elapsed_time(stop) * 1e-3)
+    assert errors.shape[0] == per_rank * world and np.isfinite(errors).all()
 
     # FP64 FMA peak of this GPU, measured (no figure for it in MEASURED_PEAKS.json)
     sink = torch.zeros(8, dtype=torch.float64, device="cuda")
@@ -401,9 +722,12 @@ def bench_search(engine, dist, world, rank, data, args):
 
     m = 2 * bandwidth + 1
     n_idx = len(indices)
-    # flops the device formulation performs per candidate: right-hand sides
-    # 2*N*M*C, harmonic recurrence + sums ~ (6+2)*N*2bw*2, solve (2/3)M^3 + 2*C*M^2
-    flops_per_cand = 2.0 * n_idx * m * n_chans + 16.0 * n_idx * 2 * bandwidth * 2 \
+    # Flops the device formulation executes per candidate: right-hand sides
+    # on the FP64 tensor cores, 2*N*(2bw)*C (the constant row comes from the column sums, once
+    # per call); harmonic generator (one complex product = 6 flops + 2 sum adds) 8*N*2bw;
+    # sincos + power table ~60*N; solve (2/3)M^3 + 2*C*M^2.
+    dmma_flops = 2.0 * n_idx * (2 * bandwidth) * n_chans
+    flops_per_cand = dmma_flops + 8.0 * n_idx * 2 * bandwidth + 60.0 * n_idx \
         + (2.0 / 3.0) * m ** 3 + 2.0 * n_chans * m * m
     reference_flops_per_cand = n_idx * (m * (m + 1) + 4.0 * n_chans * m)
     achieved = flops_per_cand * per_rank * steps / seconds / 1e12
@@ -413,32 +737,36 @@ def bench_search(engine, dist, world, rank, data, args):
         "ms_per_step": 1e3 * seconds / steps, "steps": steps,
         "config": {"workload": f"evaluator on cfg2 run-3 shape: {n_idx} random samples x {n_chans} "
                                f"channels, bandwidth {bandwidth}, {per_rank} candidates per GPU per step",
-                   "sharding": "candidates sharded, one NCCL all-gather of errors per step"
-                               if world > 1 else "single GPU"},
+                   "sharding": "_sharding.evaluate_sharded: contiguous candidate block per GPU, one "
+                               "NCCL all-gather of the errors per step; tiles standardised by channel "
+                               "block and all-gathered" if world > 1 else "single GPU"},
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak, "traffic": None,
-                     "peak_source": "measured here: parrm_fp64_fma_burn (DFMA chains on all SMs)",
+                     "dmma_frac": dmma_flops * per_rank * steps / seconds / 1e12 / fp64_peak,
+                     "peak_source": "measured here: parrm_fp64_fma_burn (scalar DFMA chains on all "
+                                    "SMs; DMMA has the same per-SM flop rate, scripts/micro/dmma_rate.cu)",
                      "flops_per_candidate": flops_per_cand,
                      "reference_flops_per_candidate": reference_flops_per_cand},
     }
     # the whole search through the public API (host array in, period out): three coarse-to-fine
-    # grid runs + lock-step Nelder-Mead, ~1 800 objective evaluations
-    from pyparrm_b200 import PARRM
-    from pyparrm_b200.synthetic import true_period
-
+    # grid runs + lock-step Nelder-Mead, ~1 800 objective evaluations; under
+    # enable_sharding() every rank uploads only its channel block and evaluates its candidates
     searcher = PARRM(data, FS, FA, verbose=False)
+    searcher.find_period(random_seed=0)  # first call builds tiles' workspace; timed call below
+    barrier(dist)
     launches0 = engine.launches
     t0 = time.perf_counter()
     searcher.find_period(random_seed=0)
-    api_seconds = time.perf_counter() - t0
+    api_seconds = max_over_ranks(dist, time.perf_counter() - t0)
     result["public_api"] = {
-        "call": "PARRM(data, 2000, 130).find_period(random_seed=0) on the 64 x 1.2M recording",
+        "call": "PARRM(data, 2000, 130).find_period(random_seed=0) on the 64 x 1.2M recording"
+                + (" under enable_sharding()" if world > 1 else ""),
         "seconds": api_seconds, "gpu_launches": engine.launches - launches0,
         "period": float(searcher.period),
         "rel_err_vs_injected_period": abs(float(searcher.period) - true_period(FS, FA))
         / true_period(FS, FA),
     }
-    if rank == 0:
+    if rank == 0 and world == 1:
         result["cpu_baseline"] = cpu_search_baseline(data, indices, grid, bandwidth)
     return result
 

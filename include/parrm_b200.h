@@ -43,6 +43,8 @@ typedef enum {
 } parrm_status_t;
 
 typedef enum { PARRM_F64 = 0, PARRM_F32 = 1 } parrm_dtype_t;
+/* what a recording may be stored as on its way in (parrm_convert widens it on the device) */
+typedef enum { PARRM_I16 = 2, PARRM_I32 = 3 } parrm_storage_t;
 
 /* filter_direction strings of PARRM.create_filter (parrm.py:710-714, 817-820) */
 typedef enum { PARRM_DIR_BOTH = 0, PARRM_DIR_PAST = 1, PARRM_DIR_FUTURE = 2 } parrm_direction_t;
@@ -67,6 +69,11 @@ int         parrm_host_is_pinned(const void* h_ptr);
  * copy synchronous with respect to the host, as CUDA defines). */
 int         parrm_copy_h2d_async(void* d_dst, const void* h_src, size_t bytes, void* stream);
 int         parrm_copy_d2h_async(void* h_dst, const void* d_src, size_t bytes, void* stream);
+/* Page-lock / release a host range in place (cudaHostRegister): a caller that filters or
+ * searches the same NumPy array repeatedly registers it once instead of having every call
+ * staged through pinned buffers (PARRM holds `data` by reference, parrm.py:124). */
+int         parrm_host_register(void* h_ptr, size_t bytes);
+int         parrm_host_unregister(void* h_ptr);
 
 /* ------------------------------------------------------------------------
  * Standardisation: PARRM._standardise_data (parrm.py:272-280)
@@ -208,6 +215,12 @@ int parrm_filter_specialise_check(const void* h_plan, int dtype,
  * crosses PCIe as float64, as the reference's API hands it over, parrm.py:866-875). */
 int parrm_convert_f64_to_f32(const double* d_src, float* d_dst, int64_t n, void* stream);
 int parrm_convert_f32_to_f64(const float* d_src, double* d_dst, int64_t n, void* stream);
+/* General form: src_type in {PARRM_F64, PARRM_F32, PARRM_I16, PARRM_I32}, dst_type in
+ * {PARRM_F64, PARRM_F32}.  The reference accepts any 2-D ndarray and widens it on the host
+ * (parrm.py:861-866, 877-886); here float32 / int16 / int32 recordings cross PCIe in their
+ * own width and are widened on the device. */
+int parrm_convert(const void* d_src, int src_type, void* d_dst, int dst_type, int64_t n,
+                  void* stream);
 
 /* Measured FP64 FMA throughput helper for the roofline denominator of the evaluator
  * (bench.py): runs `iters` dependent-chain DFMA batches on every SM; reports flops issued. */

@@ -16,6 +16,7 @@ from .data import get_example_data_paths
 _LAZY = {
     "PARRM": (".parrm", "PARRM"),
     "pinned_empty": ("._engine", "pinned_empty"),
+    "pin_array": ("._engine", "pin_array"),
     "enable_sharding": ("._sharding", "enable"),
     "disable_sharding": ("._sharding", "disable"),
 }
@@ -47,5 +48,5 @@ def install_as_pyparrm() -> None:
         sys.modules.setdefault("pyparrm." + sub, importlib.import_module("." + sub, __name__))
 
 
-__all__ = ["PARRM", "get_example_data_paths", "pinned_empty", "install_as_pyparrm",
+__all__ = ["PARRM", "get_example_data_paths", "pinned_empty", "pin_array", "install_as_pyparrm",
            "enable_sharding", "disable_sharding", "__version__"]

@@ -24,7 +24,7 @@ from . import _native
 from ._native import check, lib
 
 _CHUNK_BYTES = int(os.environ.get("PYPARRM_B200_CHUNK_MB", "32")) << 20
-_PINNED_OUT_LIMIT = int(os.environ.get("PYPARRM_B200_PINNED_OUT_MB", "4096")) << 20
+_PINNED_OUT_LIMIT = int(os.environ.get("PYPARRM_B200_PINNED_OUT_MB", "2048")) << 20
 _EVAL_WS_LIMIT = int(os.environ.get("PYPARRM_B200_EVAL_WS_MB", "1024")) << 20
 _N_SLOTS = 3
 _COPY_THREADS = max(1, min(8, (os.cpu_count() or 1)))
@@ -67,6 +67,37 @@ def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
 
 def is_pinned(array: np.ndarray) -> bool:
     return bool(lib.parrm_host_is_pinned(_vp(array.ctypes.data)))
+
+
+class pin_array:
+    """Page-lock an existing C-contiguous NumPy array in place (``cudaHostRegister``), so that
+    every later ``find_period`` / ``filter_data`` on it copies straight from the caller's
+    memory instead of staging each call through pinned buffers.  Worth it when the same
+    recording is used more than once (registering costs about as much as one staged pass).
+
+    ``handle = pin_array(data)`` ... ``handle.release()``; also a context manager.  The array
+    must stay alive and must not be resized while registered."""
+
+    def __init__(self, array: np.ndarray):
+        if not isinstance(array, np.ndarray) or not array.flags.c_contiguous:
+            raise TypeError("pin_array needs a C-contiguous NumPy array")
+        self.array = array
+        self._ptr = None
+        if array.nbytes and not is_pinned(array):
+            check(lib.parrm_host_register(_vp(array.ctypes.data), array.nbytes),
+                  "parrm_host_register")
+            self._ptr = array.ctypes.data
+
+    def release(self) -> None:
+        if self._ptr is not None:
+            check(lib.parrm_host_unregister(_vp(self._ptr)), "parrm_host_unregister")
+            self._ptr = None
+
+    def __enter__(self):
+        return self.array
+
+    def __exit__(self, *exc) -> None:
+        self.release()
 
 
 @dataclass
@@ -114,23 +145,30 @@ class DeviceEngine:
     def _empty(self, n, dtype):
         return self.torch.empty(int(n), dtype=dtype, device=self.device)
 
-    def _slots(self, in_bytes: int, out_bytes: int):
-        key = (in_bytes, out_bytes)
-        if self._ring is None or self._ring[0][0] < in_bytes or self._ring[0][1] < out_bytes:
+    def _slots(self, in_bytes: int, out_bytes: int, x_bytes: int = 0, y_bytes: int = 0):
+        """Device ring: per slot ``d_in`` (bytes as they arrive), ``d_out`` (bytes as they leave)
+        and, when the storage type differs from the compute type, ``d_x`` / ``d_y``."""
+        want = (in_bytes, out_bytes, x_bytes, y_bytes)
+        if self._ring is None or any(h < w for h, w in zip(self._ring[0], want)):
             t = self.torch
+            have = self._ring[0] if self._ring is not None else (0, 0, 0, 0)
+            sizes = tuple(max(h, w) for h, w in zip(have, want))
+            self._ring = None  # release the old ring before the new one is allocated
             slots = []
             for _ in range(_N_SLOTS):
                 slots.append(
                     dict(
-                        d_in=self._empty(max(in_bytes, 16), t.uint8),
-                        d_out=self._empty(max(out_bytes, 16), t.uint8),
+                        d_in=self._empty(max(sizes[0], 16), t.uint8),
+                        d_out=self._empty(max(sizes[1], 16), t.uint8),
+                        d_x=self._empty(max(sizes[2], 16), t.uint8),
+                        d_y=self._empty(max(sizes[3], 16), t.uint8),
                         ev_in=t.cuda.Event(),
                         ev_run=t.cuda.Event(),
                         ev_out=t.cuda.Event(),
                         used=False,
                     )
                 )
-            self._ring = (key, slots)
+            self._ring = (sizes, slots)
         for slot in self._ring[1]:
             slot["used"] = False
         return self._ring[1]
@@ -231,6 +269,24 @@ class DeviceEngine:
                 y=d_y, sumsq=(d_y * d_y).sum(0), indices=t.from_numpy(indices).to(self.device),
                 n_indices=int(y.shape[0]), n_chans=int(y.shape[1]),
             )
+
+    def merge_channel_tiles(self, tile: SearchTile, all_gather, n_chans: int, per: int) -> SearchTile:
+        """Tile of all ``n_chans`` channels from the per-rank tiles of channel blocks of ``per``
+        channels (``_sharding.prepare_tiles_sharded``): the blocks are zero-padded to ``per``
+        columns, exchanged with ``all_gather`` (-> ``[world, ...]``) and interleaved back into
+        the sample-major ``[samples, channels]`` layout."""
+        t = self.torch
+        with self._lock, t.cuda.device(self.device):
+            y = t.zeros((tile.n_indices, per), dtype=t.float64, device=self.device)
+            y[:, : tile.n_chans] = tile.y
+            sumsq = t.zeros(per, dtype=t.float64, device=self.device)
+            sumsq[: tile.n_chans] = tile.sumsq
+            ys = all_gather(y)              # [world, N, per]
+            sums = all_gather(sumsq)        # [world, per]
+            world = ys.shape[0]
+            y_all = ys.permute(1, 0, 2).reshape(tile.n_indices, world * per)[:, :n_chans]
+            return SearchTile(y=y_all.contiguous(), sumsq=sums.reshape(-1)[:n_chans].contiguous(),
+                              indices=tile.indices, n_indices=tile.n_indices, n_chans=int(n_chans))
 
     def standardise_full(self, data: np.ndarray, outlier_boundary: float) -> np.ndarray:
         """The reference's ``_standard_data`` array [C, T-1] (parrm.py:272-280), on demand."""
@@ -389,6 +445,23 @@ class DeviceEngine:
             data = np.ascontiguousarray(data)
         return data, code
 
+    _STORAGE = {"float64": _native.F64, "float32": _native.F32, "int16": _native.I16,
+                "int32": _native.I32}
+
+    def _as_storage_array(self, data: np.ndarray):
+        """``(C-contiguous array, storage code)``: float64 / float32 / int16 / int32 recordings
+        are uploaded in their own width and widened on the device (the reference widens on the
+        host, parrm.py:861-866); any other real dtype is first converted to float64 here."""
+        code = self._STORAGE.get(data.dtype.name)
+        if code is None:
+            if not (np.issubdtype(data.dtype, np.floating) or np.issubdtype(data.dtype, np.integer)
+                    or data.dtype == np.bool_):
+                raise TypeError(f"unsupported data dtype {data.dtype}")
+            data, code = data.astype(np.float64), _native.F64
+        if not data.flags.c_contiguous:
+            data = np.ascontiguousarray(data)
+        return data, code
+
     # A job of at least this many channel-samples gets the kernel specialised for its plan
     # (built once per plan, ~1 s); smaller one-off jobs keep the pre-built kernels.
     SPECIALISE_FROM = 1 << 24
@@ -443,46 +516,65 @@ class DeviceEngine:
             self.launches += 1
         return d_out
 
-    def filter_host_window(self, chunk: np.ndarray, taps: np.ndarray, x0: int, t0: int, t1: int,
-                           n_total: int) -> np.ndarray:
-        """Time shard of ``filter_data``: ``chunk`` holds samples ``[x0, x0 + chunk.shape[1])`` of
-        a recording of ``n_total`` samples (the outputs' tap-window halo included); returns the
-        outputs for global times ``[t0, t1)``.  Used when channels are fewer than ranks."""
+    def filter_shard(self, chunk: np.ndarray, taps: np.ndarray, x0: int, t0: int, t1: int,
+                     n_total: int, precision: str = "fp64"):
+        """One shard of ``filter_data``, result left on the DEVICE (float64 ``[C, t1 - t0]``):
+        ``chunk`` holds samples ``[x0, x0 + chunk.shape[1])`` of a recording of ``n_total``
+        samples (the outputs' tap-window halo included); the outputs are those of global times
+        ``[t0, t1)``.  Time shards (fewer channels than ranks) and the gather modes of
+        ``enable_sharding`` use it: the shard goes on to a collective, not to the host."""
         t = self.torch
         chunk, _ = self._as_float_array(chunk, allow_f32=False)
         n_chans, n_x = chunk.shape
+        f32 = precision == "fp32"
+        code = _native.F32 if f32 else _native.F64
         with self._lock, t.cuda.device(self.device):
-            h_plan, d_plan, _ = self._plan(taps, _native.F64)
+            h_plan, d_plan, _ = self._plan(taps, code)
             d_x = t.from_numpy(chunk).to(self.device)
-            d_out = t.empty((n_chans, t1 - t0), dtype=t.float64, device=self.device)
+            if f32:
+                d_x = d_x.to(t.float32)
+            d_out = t.empty((n_chans, t1 - t0), dtype=d_x.dtype, device=self.device)
             opts = self._filter_options(n_chans * (t1 - t0))
-            self._apply(
-                opts, _vp(d_x.data_ptr()), n_x, x0, n_x, _vp(d_out.data_ptr()), t1 - t0, t0,
-                t1 - t0, n_total, n_chans, _vp(d_plan.data_ptr()), _vp(h_plan.ctypes.data),
-                _native.F64, self._stream_ptr(t.cuda.current_stream()))
-            self.launches += 1
-            return d_out.cpu().numpy()
+            for c0 in range(0, n_chans, 65535):
+                c1 = min(c0 + 65535, n_chans)
+                self._apply(
+                    opts, _vp(d_x[c0:c1].data_ptr()), n_x, x0, n_x, _vp(d_out[c0:c1].data_ptr()),
+                    t1 - t0, t0, t1 - t0, n_total, c1 - c0, _vp(d_plan.data_ptr()),
+                    _vp(h_plan.ctypes.data), code, self._stream_ptr(t.cuda.current_stream()))
+                self.launches += 1
+            return d_out.to(t.float64)
+
+    def filter_host_window(self, chunk: np.ndarray, taps: np.ndarray, x0: int, t0: int, t1: int,
+                           n_total: int) -> np.ndarray:
+        """:meth:`filter_shard` with the result copied to the host."""
+        return self.filter_shard(chunk, taps, x0, t0, t1, n_total).cpu().numpy()
 
     def filter_host(self, data: np.ndarray, taps: np.ndarray, precision: str = "fp64",
-                    strategy: int | None = None) -> np.ndarray:
-        """``filter_data`` body (parrm.py:861-869): NumPy [C, T] in, float64 NumPy [C, T] out."""
+                    strategy: int | None = None, out_dtype=None) -> np.ndarray:
+        """``filter_data`` body (parrm.py:861-869): NumPy [C, T] in, NumPy [C, T] out (float64
+        as the reference returns it, or float32 on request).
+
+        Bytes on PCIe: the recording goes up in the caller's dtype (float64, float32, int16 or
+        int32) and is widened to the compute type on the device; the result comes back in
+        ``out_dtype``.  ``precision="fp32"`` computes in float32."""
         t = self.torch
-        data, _ = self._as_float_array(data, allow_f32=False)
+        data, in_code = self._as_storage_array(data)
+        out_np = np.dtype(np.float64 if out_dtype is None else out_dtype)
+        if out_np not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise TypeError("`out_dtype` must be float64 or float32.")
+        comp_code = _native.F32 if precision == "fp32" else _native.F64
+        out_code = _native.F64 if out_np == np.float64 else _native.F32
+        es_in, es_out = data.dtype.itemsize, out_np.itemsize
+        es_c = 4 if comp_code == _native.F32 else 8
         n_chans, n_samples = data.shape
-        out_bytes_total = n_chans * n_samples * 8
-        if 0 < out_bytes_total <= _PINNED_OUT_LIMIT:
-            out = pinned_empty((n_chans, n_samples), np.float64)
-        else:
-            out = np.empty((n_chans, n_samples), dtype=np.float64)
+        out = self._output_array((n_chans, n_samples), out_np)
         if n_chans == 0 or n_samples == 0:
             return out
-        compute_f32 = precision == "fp32"
-        code = _native.F32 if compute_f32 else _native.F64
         with self._lock, t.cuda.device(self.device):
-            h_plan, d_plan, (w_lo, w_hi) = self._plan(taps, code, strategy)
+            h_plan, d_plan, (w_lo, w_hi) = self._plan(taps, comp_code, strategy)
             opts = self._filter_options(n_chans * n_samples)
             span = w_hi - w_lo
-            row_bytes = n_samples * 8
+            row_bytes = n_samples * max(es_in, es_out)
             # chunk list: (c0, c1, t0, t1, x0, x1) -- channels [c0,c1), outputs [t0,t1), inputs [x0,x1)
             chunks = []
             if row_bytes <= 2 * _CHUNK_BYTES:
@@ -490,20 +582,22 @@ class DeviceEngine:
                 for c0 in range(0, n_chans, rows):
                     chunks.append((c0, min(c0 + rows, n_chans), 0, n_samples, 0, n_samples))
             else:
-                step = max(_CHUNK_BYTES // 8, 4 * span)
+                step = max(_CHUNK_BYTES // max(es_in, es_out), 4 * span)
                 for c in range(n_chans):
                     for t0 in range(0, n_samples, step):
                         t1 = min(t0 + step, n_samples)
                         chunks.append((c, c + 1, t0, t1, max(0, t0 - w_hi), min(n_samples, t1 - w_lo)))
-            in_bytes = max((c1 - c0) * (x1 - x0) * 8 for c0, c1, _, _, x0, x1 in chunks)
-            out_bytes = max((c1 - c0) * (t1 - t0) * 8 for c0, c1, t0, t1, _, _ in chunks)
-            slots = self._slots(in_bytes, out_bytes)
+            in_elems = max((c1 - c0) * (x1 - x0) for c0, c1, _, _, x0, x1 in chunks)
+            out_elems = max((c1 - c0) * (t1 - t0) for c0, c1, t0, t1, _, _ in chunks)
+            widen_in, narrow_out = in_code != comp_code, comp_code != out_code
+            slots = self._slots(in_elems * es_in, out_elems * es_out,
+                                in_elems * es_c if widen_in else 0,
+                                out_elems * es_c if narrow_out else 0)
             in_pinned, out_pinned = is_pinned(data), is_pinned(out)
-            stage_in = None if in_pinned else self._staging("_stage_in", in_bytes)
-            stage_out = None if out_pinned else self._staging("_stage_out", out_bytes)
+            stage_in = None if in_pinned else self._staging("_stage_in", in_elems * es_in)
+            stage_out = None if out_pinned else self._staging("_stage_out", out_elems * es_out)
             s_in, s_run, s_out = (self._stream_ptr(s) for s in (self.s_in, self.s_run, self.s_out))
             pending = [None] * _N_SLOTS  # (host dst ptr, nbytes) awaiting copy-out of staging
-            tf32 = [None] * _N_SLOTS
 
             def drain(k):
                 if pending[k] is not None:
@@ -516,58 +610,85 @@ class DeviceEngine:
                 k = i % _N_SLOTS
                 slot = slots[k]
                 n_c, n_x, n_o = c1 - c0, x1 - x0, t1 - t0
-                src = data.ctypes.data + (c0 * n_samples + x0) * 8
-                dst = out.ctypes.data + (c0 * n_samples + t0) * 8
+                src = data.ctypes.data + (c0 * n_samples + x0) * es_in
+                dst = out.ctypes.data + (c0 * n_samples + t0) * es_out
                 if slot["used"]:
                     if not in_pinned:
                         slot["ev_in"].synchronize()  # staging buffer free again
                     drain(k)
+                n_in_bytes = n_c * n_x * es_in  # whole rows, or a time window of one row
                 if not in_pinned:
-                    _threaded_memmove(stage_in[k].data_ptr(), src, n_c * n_x * 8)
+                    _threaded_memmove(stage_in[k].data_ptr(), src, n_in_bytes)
                     src = stage_in[k].data_ptr()
                 if slot["used"]:
                     self.s_in.wait_event(slot["ev_run"])   # kernel finished reading d_in
                 check(lib.parrm_copy_h2d_async(_vp(slot["d_in"].data_ptr()), _vp(src),
-                                               n_c * n_x * 8, s_in), "H2D copy")
+                                               n_in_bytes, s_in), "H2D copy")
                 slot["ev_in"].record(self.s_in)
                 self.s_run.wait_event(slot["ev_in"])
                 if slot["used"]:
                     self.s_run.wait_event(slot["ev_out"])  # previous result left d_out
-                d_in_ptr, d_out_ptr = slot["d_in"].data_ptr(), slot["d_out"].data_ptr()
-                if compute_f32:
-                    with t.cuda.stream(self.s_run):  # allocations ordered on the compute stream
-                        x32 = t.empty(n_c * n_x, dtype=t.float32, device=self.device)
-                        y32 = t.empty(n_c * n_o, dtype=t.float32, device=self.device)
-                    tf32[k] = (x32, y32)
-                    check(lib.parrm_convert_f64_to_f32(_vp(d_in_ptr), _vp(x32.data_ptr()),
-                                                       n_c * n_x, s_run), "parrm_convert_f64_to_f32")
+                d_x = slot["d_in"].data_ptr()
+                if widen_in:
+                    check(lib.parrm_convert(_vp(d_x), in_code, _vp(slot["d_x"].data_ptr()),
+                                            comp_code, n_c * n_x, s_run), "parrm_convert")
                     self.launches += 1
-                    d_in_ptr, d_out_ptr = x32.data_ptr(), y32.data_ptr()
+                    d_x = slot["d_x"].data_ptr()
+                d_y = slot["d_y"].data_ptr() if narrow_out else slot["d_out"].data_ptr()
                 self._apply(
-                    opts, _vp(d_in_ptr), n_x, x0, n_x, _vp(d_out_ptr), n_o, t0, n_o, n_samples,
-                    n_c, _vp(d_plan.data_ptr()), _vp(h_plan.ctypes.data), code, s_run)
+                    opts, _vp(d_x), n_x, x0, n_x, _vp(d_y), n_o, t0, n_o, n_samples,
+                    n_c, _vp(d_plan.data_ptr()), _vp(h_plan.ctypes.data), comp_code, s_run)
                 self.launches += 1
-                if compute_f32:
-                    check(lib.parrm_convert_f32_to_f64(_vp(tf32[k][1].data_ptr()),
-                                                       _vp(slot["d_out"].data_ptr()), n_c * n_o,
-                                                       s_run), "parrm_convert_f32_to_f64")
+                if narrow_out:
+                    check(lib.parrm_convert(_vp(d_y), comp_code, _vp(slot["d_out"].data_ptr()),
+                                            out_code, n_c * n_o, s_run), "parrm_convert")
                     self.launches += 1
                 slot["ev_run"].record(self.s_run)
                 self.s_out.wait_event(slot["ev_run"])
                 if out_pinned:
                     check(lib.parrm_copy_d2h_async(_vp(dst), _vp(slot["d_out"].data_ptr()),
-                                                   n_c * n_o * 8, s_out), "D2H copy")
+                                                   n_c * n_o * es_out, s_out), "D2H copy")
                 else:
                     check(lib.parrm_copy_d2h_async(_vp(stage_out[k].data_ptr()),
-                                                   _vp(slot["d_out"].data_ptr()), n_c * n_o * 8,
-                                                   s_out), "D2H copy")
-                    pending[k] = (dst, n_c * n_o * 8)
+                                                   _vp(slot["d_out"].data_ptr()),
+                                                   n_c * n_o * es_out, s_out), "D2H copy")
+                    pending[k] = (dst, n_c * n_o * es_out)
                 slot["ev_out"].record(self.s_out)
                 slot["used"] = True
             for k in range(_N_SLOTS):
                 drain(k)
             self.s_out.synchronize()
         return out
+
+    # Results are handed to the caller in page-locked memory (direct D2H, no staging copy) up
+    # to this many live bytes; beyond that -- many results kept alive, or huge ones -- they are
+    # ordinary pageable arrays filled through the pinned staging ring, so a caller can never
+    # page-lock more than the limit through this path.  torch's host allocator caches freed
+    # pinned blocks; when a result of a new size would push the cache past the limit the
+    # cache is emptied first.
+    def _output_array(self, shape, dtype) -> np.ndarray:
+        import weakref
+
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        live = getattr(self, "_pinned_live", 0)
+        if nbytes == 0 or live + nbytes > _PINNED_OUT_LIMIT:
+            return np.empty(shape, dtype=dtype)
+        if nbytes not in getattr(self, "_pinned_sizes", set()):
+            sizes = getattr(self, "_pinned_sizes", set())
+            if sum(sizes) + nbytes > _PINNED_OUT_LIMIT:
+                empty_cache = getattr(self.torch._C, "_host_emptyCache", None)
+                if empty_cache is not None:
+                    empty_cache()
+                sizes.clear()
+            sizes.add(nbytes)
+            self._pinned_sizes = sizes
+        out = pinned_empty(shape, dtype)
+        self._pinned_live = live + nbytes
+        weakref.finalize(out.base if out.base is not None else out, self._release_pinned, nbytes)
+        return out
+
+    def _release_pinned(self, nbytes: int) -> None:
+        self._pinned_live = max(0, getattr(self, "_pinned_live", 0) - nbytes)
 
 
 _engine: DeviceEngine | None = None
@@ -581,6 +702,11 @@ def get_engine() -> DeviceEngine:
         if _engine is None:
             _engine = DeviceEngine()
         return _engine
+
+
+def current_engine():
+    """The process-wide engine if one exists already (never creates it)."""
+    return _engine
 
 
 def set_engine(engine) -> None:

@@ -15,7 +15,7 @@ from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_size_
 LIB_NAME = "libparrm_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
-F64, F32 = 0, 1
+F64, F32, I16, I32 = 0, 1, 2, 3
 DIR_BOTH, DIR_PAST, DIR_FUTURE = 0, 1, 2
 DIRECTIONS = {"both": DIR_BOTH, "past": DIR_PAST, "future": DIR_FUTURE}
 MAX_BANDWIDTH = 23
@@ -87,6 +87,9 @@ SIGNATURES = {
     "parrm_filter_specialise_check": (
         c_int, [c_void_p, c_int, POINTER(FilterOptions), c_void_p, POINTER(c_size_t)]
     ),
+    "parrm_host_register": (c_int, [c_void_p, c_size_t]),
+    "parrm_host_unregister": (c_int, [c_void_p]),
+    "parrm_convert": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p]),
     "parrm_convert_f64_to_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "parrm_convert_f32_to_f64": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "parrm_fp64_fma_burn": (c_int, [c_int64, c_void_p, POINTER(c_double), c_void_p]),

@@ -48,6 +48,19 @@ int convert(const S* src, D* dst, int64_t n, void* stream, const char* name) {
   return PARRM_OK;
 }
 
+// Storage types a recording may arrive in (parrm_storage_t): the reference accepts any 2-D
+// ndarray (parrm.py:877-886) and widens it on the host; here the caller's bytes cross PCIe as
+// they are and are widened on the device.
+template <typename S>
+int convert_from(const S* src, void* d_dst, int dst_type, int64_t n, void* stream) {
+  if (dst_type == PARRM_F64)
+    return convert<S, double>(src, static_cast<double*>(d_dst), n, stream, "parrm_convert");
+  if (dst_type == PARRM_F32)
+    return convert<S, float>(src, static_cast<float*>(d_dst), n, stream, "parrm_convert");
+  set_error("parrm_convert: destination must be float64 or float32");
+  return PARRM_ERR_INVALID_ARGUMENT;
+}
+
 }  // namespace parrm
 
 extern "C" {
@@ -58,6 +71,31 @@ int parrm_convert_f64_to_f32(const double* d_src, float* d_dst, int64_t n, void*
 
 int parrm_convert_f32_to_f64(const float* d_src, double* d_dst, int64_t n, void* stream) {
   return parrm::convert<float, double>(d_src, d_dst, n, stream, "parrm_convert_f32_to_f64");
+}
+
+int parrm_convert(const void* d_src, int src_type, void* d_dst, int dst_type, int64_t n,
+                  void* stream) {
+  switch (src_type) {
+    case PARRM_F64: return parrm::convert_from(static_cast<const double*>(d_src), d_dst, dst_type, n, stream);
+    case PARRM_F32: return parrm::convert_from(static_cast<const float*>(d_src), d_dst, dst_type, n, stream);
+    case PARRM_I16: return parrm::convert_from(static_cast<const int16_t*>(d_src), d_dst, dst_type, n, stream);
+    case PARRM_I32: return parrm::convert_from(static_cast<const int32_t*>(d_src), d_dst, dst_type, n, stream);
+    default:
+      parrm::set_error("parrm_convert: unknown source type %d", src_type);
+      return PARRM_ERR_INVALID_ARGUMENT;
+  }
+}
+
+int parrm_host_register(void* h_ptr, size_t bytes) {
+  PARRM_REQUIRE(h_ptr != nullptr && bytes > 0, "parrm_host_register: empty range");
+  PARRM_CUDA_OK(cudaHostRegister(h_ptr, bytes, cudaHostRegisterPortable));
+  return PARRM_OK;
+}
+
+int parrm_host_unregister(void* h_ptr) {
+  PARRM_REQUIRE(h_ptr != nullptr, "parrm_host_unregister: null pointer");
+  PARRM_CUDA_OK(cudaHostUnregister(h_ptr));
+  return PARRM_OK;
 }
 
 int parrm_abi_version(void) { return PARRM_B200_ABI_VERSION; }

@@ -285,7 +285,8 @@ int parrm_filter_apply_ex(const void* d_x, int64_t ld_x, int64_t x_t0, int64_t n
     if (fits && worth) {
       const unsigned char* d_base = static_cast<const unsigned char*>(d_plan);
       const int rc = launch_comb_e(
-          shape, d_x, d_out, reinterpret_cast<const int32_t*>(d_base + hdr->count_offset),
+          shape, d_x, d_out, d_taps,
+          reinterpret_cast<const int32_t*>(d_base + hdr->count_offset),
           reinterpret_cast<const double*>(d_base + hdr->recip_offset), ld_x, x_t0, n_x, ld_out,
           t0, n_out, n_samples_total, n_chans, s, nullptr);
       if (rc == PARRM_OK) {

@@ -123,6 +123,7 @@ __host__ __device__ constexpr int minus_tap(int i) {
 struct Args {
   const T* x;
   T* out;
+  const int32_t* taps;   // plan: the NTAPS tap offsets, ascending (rare path only)
   const int32_t* count;  // plan table: count[v - (WLO - 1)] = #{taps <= v}, WLO - 1 <= v <= WHI
   const T2* recip;       // plan table: 0, 1/1, 1/2, ... 1/NTAPS (float64)
   int64_t ld_x, x_t0, n_x;
@@ -194,6 +195,28 @@ __device__ __forceinline__ T edge_value(const int32_t* __restrict__ count,
   return y;
 }
 
+// Rare path: an output whose fast value came out non-finite is re-evaluated tap by tap from
+// global memory, exactly as the definition reads (parrm.py:861-869): mean over the in-range
+// taps, 0 when that is not finite.  This is what makes a NaN / Inf sample zero exactly the
+// outputs whose tap window (or own sample) holds it, even where the plan covers a non-tap
+// offset with a box and cancels it with a -1 term (NaN - NaN does not cancel).  It runs after
+// the piece, over the span of steps the step loop flagged, so that the loop itself holds no
+// call (a call in a cold branch still makes the compiler rebuild addresses after the join).
+__device__ __noinline__ T direct_value(const Args& a, const T* __restrict__ xrow, int64_t t,
+                                       int64_t lo_valid, int64_t hi_valid) {
+  T acc = T(0);
+  int n_in = 0;
+  for (int k = 0; k < NTAPS; ++k) {
+    const int64_t g = t - a.taps[k];
+    if (g < 0 || g >= a.n_total) continue;
+    ++n_in;
+    if (g >= lo_valid && g < hi_valid) acc += xrow[g];
+  }
+  if (n_in == 0) return T(0);
+  const T y = xrow[t] - acc * T(a.recip[n_in]);
+  return fabs(y) <= a.t_max ? y : T(0);
+}
+
 // A consumer thread's position in the chunk sequence of its piece.
 struct Walk {
   int pb;           // byte offset (from smem_raw) of the sample HB*CH before the group's first output
@@ -256,13 +279,15 @@ __device__ __forceinline__ T ring_sum1(const Rings& r, int s) {
 //
 // Non-finite samples: the fast path only tests the finished output.  A NaN/Inf that entered a
 // running sum keeps it non-finite, so the test fails on every step until the bad pattern
-// value has left the ring; on those (rare) steps the sums are re-added from the rings, which
-// makes the first output past the window exact again and leaves the ones inside it 0.
+// value has left the ring; on those (rare) steps the sums are re-added from the rings (which
+// makes the first output past the window exact again) and the output itself is re-evaluated
+// tap by tap (direct_value).
 template <bool FAST>
 __device__ __forceinline__ int run_block(Rings& r, Walk& w, const Args& a,
                                          const unsigned char* const smem, uint32_t bars,
                                          int lane, int c, bool lane_stores, T* const orow,
-                                         int64_t Tb, int g, int n_groups) {
+                                         int& bad_lo, int& bad_hi, int64_t Tb, int g,
+                                         int n_groups) {
   const T neg_inv_n = a.neg_inv_n;
   const T t_max = a.t_max;
   T* const op = orow + Tb + c;  // output of step 0 of the block
@@ -330,8 +355,9 @@ __device__ __forceinline__ int run_block(Rings& r, Walk& w, const Args& a,
         if (__builtin_expect(!(fabs(y) <= t_max), 0)) {
           r.S0 = ring_sum0(r, s);
           r.S1 = ring_sum1(r, s);
-          y = fma(r.S0 + r.S1 + single, neg_inv_n, xc);
-          if (!(fabs(y) <= t_max)) y = T(0);
+          bad_lo = min(bad_lo, g * U + s);
+          bad_hi = max(bad_hi, g * U + s);
+          y = T(0);
         }
         if (lane_stores) op[s * D] = y;
       } else if (mode != 0) {
@@ -340,9 +366,9 @@ __device__ __forceinline__ int run_block(Rings& r, Walk& w, const Args& a,
         if (__builtin_expect(!(fabs(y) <= t_max), 0)) {
           r.S0 = ring_sum0(r, s);
           r.S1 = ring_sum1(r, s);
-          tot = r.S0 + r.S1 + single;
-          y = mode == 1 ? fma(tot, neg_inv_n, xc) : edge_value(a.count, a.recip, t, a.n_total, xc, tot);
-          if (!(fabs(y) <= t_max)) y = T(0);
+          bad_lo = min(bad_lo, g * U + s);
+          bad_hi = max(bad_hi, g * U + s);
+          y = T(0);
         }
         if (lane_stores && t >= a.t0 && t < a.t0 + a.n_out) op[s * D] = y;
       }
@@ -455,6 +481,7 @@ extern "C" __global__ void __launch_bounds__(NT, PE_CTAS) parrm_filter_comb_e(co
     w.rslot = rslot;
     w.fslot = fslot;
     w.fphase = fphase;
+    int bad_lo = 1 << 30, bad_hi = -1;  // span of steps whose fast output was not finite
     for (int g = 0; g < n_groups;) {
       const int64_t Tb = T0 + int64_t(g) * CH;
       // fresh sums from the rings (bounds the drift of the running update)
@@ -464,14 +491,23 @@ extern "C" __global__ void __launch_bounds__(NT, PE_CTAS) parrm_filter_comb_e(co
                         Tb + int64_t(B) * D - WLO <= a.n_total && Tb >= a.t0 &&
                         Tb + int64_t(B) * D <= a.t0 + a.n_out;
       if (fast) {
-        g += run_block<true>(r, w, a, smem_raw, bars, lane, c, lane_stores, orow, Tb, g, n_groups);
+        g += run_block<true>(r, w, a, smem_raw, bars, lane, c, lane_stores, orow, bad_lo, bad_hi,
+                             Tb, g, n_groups);
       } else {
-        g += run_block<false>(r, w, a, smem_raw, bars, lane, c, lane_stores, orow, Tb, g, n_groups);
+        g += run_block<false>(r, w, a, smem_raw, bars, lane, c, lane_stores, orow, bad_lo,
+                              bad_hi, Tb, g, n_groups);
       }
     }
     rslot = w.rslot;
     fslot = w.fslot;
     fphase = w.fphase;
+    if (lane_stores) {  // rare: re-evaluate the flagged span by the definition
+      for (int k = bad_lo; k <= bad_hi; ++k) {
+        const int64_t t = T0 + c + int64_t(k) * D;
+        if (t >= a.t0 && t < a.t0 + a.n_out)
+          orow[t] = direct_value(a, xrow, t, lo_valid, hi_valid);
+      }
+    }
     // release the rest of the window (chunks the last group still held)
     __syncwarp();
     for (int i = 0; i < HB + HF; ++i) {

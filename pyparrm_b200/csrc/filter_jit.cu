@@ -334,8 +334,8 @@ std::string comb_e_key(const CombEShape& s, int dev) {
 
 // Launches the specialised kernel (building it on first use).  PARRM_ERR_UNSUPPORTED means
 // "could not specialise here"; the caller falls back to the pre-built kernels.
-int launch_comb_e(const CombEShape& s, const void* d_x, void* d_out, const int32_t* d_count,
-                  const double* d_recip,
+int launch_comb_e(const CombEShape& s, const void* d_x, void* d_out, const int32_t* d_taps,
+                  const int32_t* d_count, const double* d_recip,
                   int64_t ld_x, int64_t x_t0, int64_t n_x, int64_t ld_out, int64_t t0,
                   int64_t n_out, int64_t n_total, int64_t n_chans, cudaStream_t stream,
                   int* regs_out) {
@@ -358,13 +358,14 @@ int launch_comb_e(const CombEShape& s, const void* d_x, void* d_out, const int32
   struct Args {
     const void* x;
     void* out;
+    const int32_t* taps;
     const int32_t* count;
     const double* recip;
     int64_t ld_x, x_t0, n_x, ld_out, t0, n_out, n_total, total_groups;
     int32_t groups_per_chan, pad;
     unsigned char consts[16];  // T neg_inv_n, t_max in the kernel's element type
   } a;
-  a.x = d_x; a.out = d_out; a.count = d_count; a.recip = d_recip;
+  a.x = d_x; a.out = d_out; a.taps = d_taps; a.count = d_count; a.recip = d_recip;
   a.ld_x = ld_x; a.x_t0 = x_t0; a.n_x = n_x;
   a.ld_out = ld_out; a.t0 = t0; a.n_out = n_out; a.n_total = n_total;
   const int64_t ch = k.chunk;

@@ -33,8 +33,8 @@ bool comb_e_shape(const FilterPlanHeader* hdr, const int32_t* terms, int dtype,
 std::string comb_e_key(const CombEShape& s, int dev);
 bool comb_e_cached(const CombEShape& s);
 int comb_e_compile_only(const CombEShape& s, size_t* cubin_bytes);
-int launch_comb_e(const CombEShape& s, const void* d_x, void* d_out, const int32_t* d_count,
-                  const double* d_recip,
+int launch_comb_e(const CombEShape& s, const void* d_x, void* d_out, const int32_t* d_taps,
+                  const int32_t* d_count, const double* d_recip,
                   int64_t ld_x, int64_t x_t0, int64_t n_x, int64_t ld_out, int64_t t0,
                   int64_t n_out, int64_t n_total, int64_t n_chans, cudaStream_t stream,
                   int* regs_out);

@@ -93,6 +93,7 @@ class PARRM:
 
     _precision = "fp64"
     _standardised = False
+    filter_shard = None  # (c0, c1, t0, t1) computed by this rank in the last filter_data()
 
     def __init__(self, data, sampling_freq, artefact_freq, verbose=True, *, precision="fp64"):
         self._check_init_inputs(data, sampling_freq, artefact_freq, verbose)
@@ -257,7 +258,11 @@ class PARRM:
         index_sets = [
             self._get_centre_indices(use_n, ignore, random_state) for use_n, ignore, _ in plan
         ]
-        tiles = engine.prepare_tiles(self._data, index_sets, self._outlier_boundary)
+        if _sharding.active():  # every rank standardises its channel block; tiles all-gathered
+            tiles = _sharding.prepare_tiles_sharded(
+                engine, self._data, index_sets, self._outlier_boundary)
+        else:
+            tiles = engine.prepare_tiles(self._data, index_sets, self._outlier_boundary)
 
         estimated_period = self._assumed_periods
         for run_idx, ((_, _, bandwidth), indices, tile) in enumerate(
@@ -319,8 +324,11 @@ class PARRM:
         ``pyparrm_b200.enable_sharding()`` the candidates are split over the ranks and the fit
         errors exchanged with one all-gather."""
         if _sharding.active():
+            engine = _engine.get_engine()
+            # device engine: the block's errors stay on the GPU through the all-gather
+            evaluate = getattr(engine, "evaluate_device", engine.evaluate)
             return _sharding.evaluate_sharded(
-                lambda block: self._evaluate(block, tile, bandwidth, lambda_), periods
+                lambda block: evaluate(tile, block, bandwidth, lambda_, self._n_chans), periods
             )
         return self._evaluate(periods, tile, bandwidth, lambda_)
 
@@ -482,12 +490,19 @@ class PARRM:
         filter_[half_width] = 1
         self._filter = filter_
 
-    def filter_data(self, data=None) -> np.ndarray:
+    def filter_data(self, data=None, *, out_dtype=None) -> np.ndarray:
         """Apply the PARRM filter and return the result (reference parrm.py:835-875).
 
-        Output is float64 ``[channels, times]``.  Where no tap falls inside the recording
+        Output is float64 ``[channels, times]`` (``out_dtype=numpy.float32``, keyword-only and
+        additive, halves the bytes that come back over PCIe).  float32 / int16 / int32
+        recordings are uploaded in their own width and widened on the device.  Where no tap falls inside the recording
         (first / last samples of a one-sided filter) the result is 0, the documented intent of
-        parrm.py:867-869 (the reference's FFT path returns rounding noise there)."""
+        parrm.py:867-869 (the reference's FFT path returns rounding noise there).
+
+        Under ``pyparrm_b200.enable_sharding()`` every rank filters its channel block (time
+        block when channels are fewer than ranks, halos read from the recording); what comes
+        back follows the ``gather`` mode given there, and ``filter_shard`` holds the
+        ``(c0, c1, t0, t1)`` range this rank computed."""
         if self._verbose:
             print("Filtering the data...")
         if self._filter is None:
@@ -498,7 +513,15 @@ class PARRM:
         data = self._check_sort_filter_data_inputs(data)
         half_width = (self._filter.shape[0] - 1) // 2
         taps = (np.flatnonzero(self._filter < 0) - half_width).astype(np.int32)
-        self._filtered_data = _engine.get_engine().filter_host(data, taps, self._precision)
+        engine = _engine.get_engine()
+        if _sharding.active():
+            out, self.filter_shard, _ = _sharding.filter_sharded(
+                engine, data, taps, self._precision, _sharding.gather_mode(), out_dtype)
+            self._filtered_data = out
+        else:
+            self.filter_shard = (0, data.shape[0], 0, data.shape[1])
+            self._filtered_data = engine.filter_host(data, taps, self._precision,
+                                                     out_dtype=out_dtype)
         if self._verbose:
             print("    ... Data filtered\n")
         return self._filtered_data

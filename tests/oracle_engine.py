@@ -30,6 +30,14 @@ class OracleEngine:
         z = oracle.standardise(data, outlier_boundary)
         return [OracleTile(z, np.asarray(idx), len(idx), z.shape[0]) for idx in index_sets]
 
+    def merge_channel_tiles(self, tile, all_gather, n_chans, per):
+        import torch
+
+        z = np.zeros((per, tile.z.shape[1]))
+        z[: tile.n_chans] = tile.z
+        z_all = all_gather(torch.from_numpy(z)).numpy().reshape(-1, z.shape[1])[:n_chans]
+        return OracleTile(z_all, tile.indices, tile.n_indices, n_chans)
+
     def tile_from_standardised(self, z, indices):
         return OracleTile(np.asarray(z), np.asarray(indices), len(indices), z.shape[0])
 
@@ -48,8 +56,12 @@ class OracleEngine:
     def build_taps(self, period, phw, hw, omit, direction):
         return oracle.tap_offsets(period, phw, hw, omit, direction)
 
-    def filter_host(self, data, taps, precision="fp64"):
-        return oracle.apply_filter_direct(np.asarray(data, dtype=np.float64), taps)
+    def filter_host(self, data, taps, precision="fp64", strategy=None, out_dtype=None):
+        out = oracle.apply_filter_direct(np.asarray(data, dtype=np.float64), taps)
+        return out if out_dtype is None else out.astype(out_dtype)
+
+    def filter_shard(self, chunk, taps, x0, t0, t1, n_total, precision="fp64"):
+        return self.filter_host_window(chunk, taps, x0, t0, t1, n_total)
 
     def filter_host_window(self, chunk, taps, x0, t0, t1, n_total):
         """Time shard: zero-pad the chunk into place and keep the requested outputs."""

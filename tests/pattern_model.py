@@ -106,12 +106,18 @@ class PatternModel:
 
                         y = value(sum(sums) + single)
                         bad = ~np.isfinite(y)
-                        if bad.any():  # sums re-added from the rings, for the chains that need it
+                        if bad.any():
+                            # sums re-added from the rings for the chains that need it; the
+                            # flagged outputs are re-evaluated tap by tap (direct_value)
                             for k, (r, m) in enumerate(zip(rings, self.m)):
                                 fresh = sum(r[(s + self.b - i) % self.b] for i in range(m))
                                 sums[k] = np.where(bad, fresh, sums[k])
-                            y2 = value(sum(sums) + single)
-                            y = np.where(bad, np.where(np.isfinite(y2), y2, 0.0), y)
+                            src = t[bad][:, None] - self.taps[None, :]
+                            inside = (src >= 0) & (src < n_total)
+                            acc = np.where(inside, sample(src), 0.0).sum(axis=1)
+                            n_in = inside.sum(axis=1)
+                            y2 = np.where(n_in > 0, xc[bad] - acc * self.recip[n_in], 0.0)
+                            y[bad] = np.where(np.isfinite(y2), y2, 0.0)
                         keep = (t >= t0) & (t < t0 + n_out)
                         out[t[keep] - t0] = y[keep]
                     g += self.gpb

@@ -228,3 +228,137 @@ def test_baseline_config_shapes(gpu_engine, name, fs, fa, n_chans, n, hw, direct
     want = oracle.apply_filter_direct(x[:2], taps)
     assert rel_err(out[:2], want, np.abs(x).max()) <= 1e-13
     assert rel_err(ref[:2], want, np.abs(x).max()) <= 1e-13
+
+
+# ---------------------------------------------------------------------------------------------
+# Run-time specialised kernel (filter_comb_e.cuh through NVRTC), forced at small sizes
+SPECIALISED_CASES = {
+    "cfg2": (2000 / 130 * (1 + 3e-6), None, 2000, 0, "both"),
+    "cfg3": (1000 / 145 * (1 + 3e-6), None, 2469, 0, "both"),
+    "cfg4 past": (30000 / 130 * (1 + 3e-6), None, 2311, 0, "past"),
+    "cfg4 future": (30000 / 130 * (1 + 3e-6), None, 2311, 0, "future"),
+    "cfg1": (1.3311148014466094, 0.01, 2000, 20, "both"),
+    "cfg2 past, omit": (2000 / 130 * (1 + 3e-6), None, 1500, 300, "past"),
+}
+
+
+def _case_taps(name):
+    period, phw, hw, omit, direction = SPECIALISED_CASES[name]
+    return oracle.tap_offsets(period, period / 50 if phw is None else phw, hw, omit, direction)
+
+
+@pytest.mark.parametrize("name", list(SPECIALISED_CASES))
+def test_specialised_kernel_against_oracle(gpu_engine, name):
+    """Interior blocks, recording edges, recordings shorter than the tap window, one strip and
+    many strips -- against the oracle's tap-by-tap sum, and fp32 storage within 1e-4."""
+    import torch
+
+    taps = _case_taps(name)
+    rng = np.random.default_rng(len(name))
+    for shape in [(3, 50_000), (1, 7001), (2, 1999), (5, 20_011), (160, 30_000)]:
+        x = rng.standard_normal(shape) * 3 + 10
+        want = oracle.apply_filter_direct(x, taps)
+        d_x = torch.from_numpy(x).cuda()
+        got = gpu_engine.filter_device(d_x, taps, kernel=_native.KERNEL_SPECIALISED)
+        assert gpu_engine.last_filter_kernel == "parrm_filter_comb_e"
+        assert rel_err(got.cpu().numpy(), want, np.abs(x).max()) <= 1e-13, (name, shape)
+    got32 = gpu_engine.filter_device(d_x.float(), taps, kernel=_native.KERNEL_SPECIALISED)
+    assert rel_err(got32.double().cpu().numpy(), want, np.abs(x).max()) <= RTOL32
+
+
+def test_specialised_kernel_alignment_and_windows(gpu_engine):
+    """Rows that start on odd elements (the TMA source must be 16-byte aligned: the chunk grid
+    shifts per row) and output ranges inside a longer recording (time shards)."""
+    import torch
+
+    taps = _case_taps("cfg2")
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((4, 30_001))
+    buf = torch.zeros(4 * 30_003 + 1, dtype=torch.float64, device="cuda")
+    d_x = buf[1:].as_strided((4, 30_001), (30_003, 1))
+    d_x.copy_(torch.from_numpy(x))
+    got = gpu_engine.filter_device(d_x, taps, kernel=_native.KERNEL_SPECIALISED).cpu().numpy()
+    assert rel_err(got, oracle.apply_filter_direct(x, taps), np.abs(x).max()) <= 1e-13
+    # time shard through the C ABI's x_t0 / t0 / n_out arguments, specialised kernel forced
+    import os
+
+    x = make_recording(1, 200_003, 2000, 130, seed=3)
+    want = oracle.apply_filter_direct(x, taps)
+    os.environ["PYPARRM_B200_FILTER_KERNEL"] = str(_native.KERNEL_SPECIALISED)
+    try:
+        for t0, t1 in ((0, 70_001), (70_001, 150_000), (150_000, 200_003)):
+            x0, x1 = max(0, t0 - 2000), min(x.shape[1], t1 + 2000)
+            got = gpu_engine.filter_host_window(x[:, x0:x1], taps, x0, t0, t1, x.shape[1])
+            assert gpu_engine.last_filter_kernel == "parrm_filter_comb_e"
+            assert rel_err(got, want[:, t0:t1], np.abs(x).max()) <= 1e-13
+    finally:
+        del os.environ["PYPARRM_B200_FILTER_KERNEL"]
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg4 past"])
+def test_non_finite_samples_zero_their_window_only(gpu_engine, name):
+    """parrm.py:869 replaces non-finite outputs by 0.  Here a NaN / Inf sample zeroes exactly
+    the outputs whose tap window (or own sample) contains it -- in both kernels -- and every
+    other output is unaffected; a 1e12 outlier only costs rounding.  (The reference's FFT
+    convolution spreads one NaN over the whole channel and so zeroes the channel: the
+    per-output rule is what its isfinite test expresses.)"""
+    import torch
+
+    taps = _case_taps(name)
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((3, 60_000))
+    x[0, 12_345] = np.nan
+    x[1, 30_000] = np.inf
+    x[1, 30_007] = -np.inf
+    x[2, 5] = 1e12
+    with np.errstate(invalid="ignore"):
+        want = oracle.apply_filter_direct(x, taps)
+    want[~np.isfinite(want)] = 0.0
+    d_x = torch.from_numpy(x).cuda()
+    outs = {}
+    for kern in (_native.KERNEL_SPECIALISED, _native.KERNEL_GATHER):
+        got = gpu_engine.filter_device(d_x, taps, kernel=kern).cpu().numpy()
+        assert np.isfinite(got).all()
+        assert np.array_equal(got[:2] == 0, want[:2] == 0), gpu_engine.last_filter_kernel
+        assert np.abs(got[:2] - want[:2]).max() <= 1e-12
+        assert np.abs(got[2] - want[2]).max() <= 1e-3       # rounding of a 1e12 outlier
+        assert np.abs(got[2, 10_000:] - want[2, 10_000:]).max() <= 1e-12   # gone past its window
+        outs[kern] = got
+    assert np.array_equal(outs[_native.KERNEL_SPECIALISED][:2] == 0,
+                          outs[_native.KERNEL_GATHER][:2] == 0)
+
+
+def test_storage_dtypes_cross_pcie_as_they_are(gpu_engine):
+    """float32 / int16 / int32 recordings are uploaded in their own width and widened on the
+    device; the result equals filtering the widened recording (the reference widens on the
+    host, parrm.py:861-866).  ``out_dtype=float32`` and the fp32 mode stay within 1e-4."""
+    from pyparrm_b200 import pin_array
+
+    taps = _case_taps("cfg2")
+    rng = np.random.default_rng(2)
+    base = rng.standard_normal((5, 40_000)) * 300
+    for dtype in (np.float32, np.int16, np.int32, np.int64, np.float64):
+        x = base.astype(dtype)
+        want = oracle.apply_filter_direct(x.astype(np.float64), taps)
+        out = gpu_engine.filter_host(x, taps)
+        assert out.dtype == np.float64
+        assert rel_err(out, want, np.abs(base).max()) <= 1e-13, dtype
+        out32 = gpu_engine.filter_host(x, taps, out_dtype=np.float32)
+        assert out32.dtype == np.float32
+        assert rel_err(out32.astype(np.float64), want, np.abs(base).max()) <= RTOL32
+        fast = gpu_engine.filter_host(x, taps, precision="fp32", out_dtype=np.float32)
+        assert rel_err(fast.astype(np.float64), want, np.abs(base).max()) <= RTOL32
+    # registering the caller's array in place: same numbers, direct copies
+    x = base.copy()
+    with pin_array(x) as pinned:
+        from pyparrm_b200._engine import is_pinned
+
+        assert is_pinned(pinned)
+        out = gpu_engine.filter_host(pinned, taps)
+    assert rel_err(out, oracle.apply_filter_direct(base, taps), np.abs(base).max()) <= 1e-13
+    parrm = PARRM(base.astype(np.int16), 2000, 130, verbose=False)
+    parrm._period = np.float64(2000 / 130 * (1 + 3e-6))
+    parrm.create_filter(filter_half_width=2000)
+    got = parrm.filter_data(out_dtype=np.float32)
+    want = oracle.apply_filter_direct(base.astype(np.int16).astype(np.float64), taps)
+    assert got.dtype == np.float32 and rel_err(got.astype(np.float64), want, 1e3) <= RTOL32

@@ -66,11 +66,39 @@ def _worker(rank, world, port, result_path):
 
         # filter: channel shards, then time shards (1 channel over 2 ranks), no collective
         taps = oracle.tap_offsets(p1.period, p1.period / 50, 300, 0, "both")
-        out, (c0, c1, t0, t1) = _sharding.filter_sharded(engine, data, taps)
+        out, (c0, c1, t0, t1), _ = _sharding.filter_sharded(engine, data, taps)
         want = oracle.apply_filter_direct(data, taps)
         chan_ok = np.array_equal(out, want[c0:c1, t0:t1]) and (c1 - c0, t1 - t0) == (1, 6000)
-        out1, (c0, c1, t0, t1) = _sharding.filter_sharded(engine, data[:1], taps)
+        out1, (c0, c1, t0, t1), _ = _sharding.filter_sharded(engine, data[:1], taps)
         time_ok = np.allclose(out1, want[c0:c1, t0:t1], rtol=0, atol=1e-12) and t1 - t0 == 3000
+        # through the public API: stitched result on rank 0 ("rank0"), everywhere ("all"),
+        # own shard only ("none"); three channels over two ranks = uneven blocks
+        data3 = make_recording(3, 4000, 200, 13, seed=6)
+        want3 = oracle.apply_filter_direct(data3, taps)
+        for mode in ("rank0", "all", "none"):
+            enable_sharding(gather=mode)
+            p3 = PARRM(data3, 200, 13, verbose=False)
+            p3._period = p1.period
+            p3.create_filter(300, 0, "both")
+            got = p3.filter_data()
+            c0, c1, t0, t1 = p3.filter_shard
+            full = mode == "all" or (mode == "rank0" and rank == 0)
+            ref = want3 if full else want3[c0:c1, t0:t1]
+            chan_ok = chan_ok and got.shape == ref.shape and np.allclose(got, ref, rtol=0, atol=1e-12)
+        # one channel over two ranks through the API (time shards + halos), stitched everywhere
+        enable_sharding(gather="all")
+        p4 = PARRM(data3[:1], 200, 13, verbose=False)
+        p4._period = p1.period
+        p4.create_filter(300, 0, "both")
+        time_ok = time_ok and np.allclose(p4.filter_data(), want3[:1], rtol=0, atol=1e-12)
+        # winner of a sweep with one (error, index) pair per rank
+        sweep = p1.period * (1 + np.linspace(-1e-3, 1e-3, 31))
+        z = oracle.standardise(data, 3.0)
+        idx = np.arange(100, 1100)
+        tile = engine.tile_from_standardised(z, idx)
+        errs = engine.evaluate(tile, sweep, 5, 1.0, 2)
+        best = _sharding.minloc_sharded(lambda blk: engine.evaluate(tile, blk, 5, 1.0, 2), sweep)
+        chan_ok = chan_ok and best == (int(np.argmin(errs)), float(errs.min()))
 
         gathered = [None] * world
         dist.all_gather_object(gathered, (float(p0.period), float(p1.period), calls_unsharded,
