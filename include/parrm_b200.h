@@ -94,6 +94,10 @@ int parrm_standardise_gather(const void* d_x, int64_t n_chans, int64_t n_samples
                              const double* d_scale, double outlier_boundary,
                              double* d_y, int64_t ld_y, double* d_sumsq,
                              int dtype, void* stream);
+/* d_sumsq[c] = sum_j d_y[j * ld_y + c]^2 for a tile the caller standardised itself (the
+ * `_optimise_local(period, data, indices, ...)` seam, parrm.py:552-559). */
+int parrm_channel_sumsq(const double* d_y, int64_t ld_y, int64_t n_chans, int64_t n_indices,
+                        double* d_sumsq, void* stream);
 /* Full z[c, 0..n_samples-2] (the `_standard_data` attribute), same dtype as x. */
 int parrm_standardise_full(const void* d_x, int64_t n_chans, int64_t n_samples, int64_t ld,
                            const double* d_scale, double outlier_boundary,
@@ -221,6 +225,64 @@ int parrm_convert_f32_to_f64(const float* d_src, double* d_dst, int64_t n, void*
  * own width and are widened on the device. */
 int parrm_convert(const void* d_src, int src_type, void* d_dst, int dst_type, int64_t n,
                   void* stream);
+
+/* ------------------------------------------------------------------------
+ * Device-resident Nelder-Mead: the scipy.optimize.fmin refinements of find_period
+ * (parrm.py:499-517, 545-550; SciPy 1.18 _minimize_neldermead, N = 1, defaults) as a state
+ * machine on the device.  A round is
+ *     parrm_eval_periods(d_points[5 * n_chains] -> d_values[5 * n_chains]);  parrm_nm_step(...)
+ * with no host involvement, so rounds can be captured into a CUDA graph; *d_n_active (written
+ * by every step) is the number of chains still running.  d_state holds n_chains records of
+ * PARRM_NM_STATE_BYTES: { double sim[2], fsim[2], points[5]; int32 fcalls, iterations, done,
+ * started } -- x = sim[0], fval = min(fsim), as fmin(..., full_output=True) reports them.
+ * parrm_nm_init writes the initial simplex {x0, 1.05 x0} to d_points slots 0 and 1 of each
+ * chain (slots 2-4 repeat x0); the first parrm_nm_step consumes those two values.
+ * ---------------------------------------------------------------------- */
+#define PARRM_NM_STATE_BYTES 88
+int parrm_nm_init(const double* d_starts, int32_t n_chains, void* d_state, double* d_points,
+                  void* stream);
+int parrm_nm_step(void* d_state, int32_t n_chains, const double* d_values, double* d_points,
+                  double xtol, double ftol, int32_t maxiter, int32_t maxfun, int32_t* d_n_active,
+                  void* stream);
+
+/* ------------------------------------------------------------------------
+ * Parameter sweeps (the explorer's loop, _utils/_plotting.py:568-584): many
+ * (period, period_half_width, filter_half_width, omit_n_samples, direction) sets at once.
+ *   parrm_default_half_width  -- PARRM._get_filter_half_width (parrm.py:788-801) per set:
+ *       d_limit[s] = (n_samples - 1) // 2; result int64 per set.
+ *   parrm_build_taps_batch    -- parrm_build_taps per set, ONE launch; row s of d_taps
+ *       (stride >= 2 * max half-width + 1) holds d_n_taps[s] ascending offsets.
+ *   parrm_filter_apply_batch  -- filter the same [n_chans, n_samples] recording with every
+ *       set in ONE launch, taking taps and counts straight from the device buffers above:
+ *       d_out[s * set_stride + c * ld_out + t].  Direct gather; for the short recordings a
+ *       sweep looks at (max_half_width bounded by shared memory: ~10^4 samples).
+ * All parameter arrays are device arrays of n_sets entries.
+ * ---------------------------------------------------------------------- */
+int parrm_default_half_width(const double* d_period, const double* d_period_half_width,
+                             const int64_t* d_omit_n_samples, const int64_t* d_limit,
+                             int64_t n_sets, int64_t* d_half_width, void* stream);
+int parrm_build_taps_batch(const double* d_period, const double* d_period_half_width,
+                           const int64_t* d_filter_half_width, const int64_t* d_omit_n_samples,
+                           const int32_t* d_direction, int64_t n_sets, int32_t* d_taps,
+                           int64_t stride, int32_t* d_n_taps, void* stream);
+int parrm_filter_apply_batch(const void* d_x, int64_t ld_x, int64_t n_samples, int64_t n_chans,
+                             const int32_t* d_taps, int64_t tap_stride, const int32_t* d_n_taps,
+                             int64_t n_sets, int64_t max_half_width, void* d_out, int64_t ld_out,
+                             int64_t set_stride, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Periodogram: compute_psd (src/pyparrm/_utils/_power.py:10-68), the spectrum the parameter
+ * explorer draws after every re-filter (_utils/_plotting.py:568-584, 637-642).
+ *   X = fft(float32(x[c, :n_points]), n_points)   (cropped or zero-padded, as scipy.fft.fft)
+ *   d_psd[c, k-1] = float32(|X_k|)^2 / (sampling_freq * n_points),  k = 1 .. n_points/2
+ * float32 output [n_chans, ld_psd >= n_points/2]; the reference's `psd[:-1] *= 2` (which
+ * doubles all ROWS but the last of a 2-D array) is left to the host wrapper.  Takes the
+ * filtered recording where it already is -- on the device -- so the explorer's
+ * filter -> spectrum loop never returns the full array to the host.
+ * ---------------------------------------------------------------------- */
+int parrm_periodogram(const void* d_x, int64_t n_chans, int64_t n_samples, int64_t ld, int dtype,
+                      int64_t n_points, double sampling_freq, float* d_psd, int64_t ld_psd,
+                      void* stream);
 
 /* Measured FP64 FMA throughput helper for the roofline denominator of the evaluator
  * (bench.py): runs `iters` dependent-chain DFMA batches on every SM; reports flops issued. */

@@ -318,6 +318,34 @@ def golden_filter_edges(ref):
     print(f"filter_edges: {case} cases")
 
 
+def golden_psd(ref):
+    """compute_psd (src/pyparrm/_utils/_power.py:10-68) on seeded inputs: the reference
+    function itself, imported from the unmodified package."""
+    from pyparrm._utils._power import compute_psd
+
+    rng = np.random.default_rng(44)
+    out = {}
+    cases = [  # shape, sampling_freq, n_points, max_freq
+        ((2, 100), 20, 10, None), ((1, 100), 20, 10, 8.0), ((3, 5000), 1000, 200, 300.0),
+        ((2, 300), 200, 1024, None), ((100,), 20, 16, None), ((4, 19130), 200, 40, 60.0),
+        ((1, 20000), 2000, 4000, None),
+    ]
+    for k, (shape, fs, n, fmax) in enumerate(cases):
+        x = rng.standard_normal(shape) * 3 + np.sin(np.arange(shape[-1]) * 0.7)
+        freqs, psd = compute_psd(data=x, sampling_freq=fs, n_points=n, max_freq=fmax)
+        if x.shape[-1] > 6000:  # only the first n_points samples matter: keep the fixture small
+            x = np.ascontiguousarray(x[..., : n + 7])
+            assert np.array_equal(compute_psd(data=x, sampling_freq=fs, n_points=n, max_freq=fmax)[1], psd)
+        out[f"case{k}_x"] = x
+        out[f"case{k}_args"] = np.array([fs, n, -1.0 if fmax is None else fmax])
+        out[f"case{k}_freqs"] = freqs
+        out[f"case{k}_psd"] = psd
+    out["n_cases"] = np.int64(len(cases))
+    out.update(meta())
+    np.savez_compressed(os.path.join(GOLDEN, "psd.npz"), **out)
+    print(f"psd: {len(cases)} cases")
+
+
 def copy_example_recordings(ref):
     os.makedirs(DATA_DST, exist_ok=True)
     for name in ref.data.DATASETS:
@@ -333,7 +361,7 @@ def main():
     jobs = dict(
         data=copy_example_recordings, taps=golden_taps, edges=golden_filter_edges,
         objective=golden_objective, example=golden_example_dbs,
-        synthetic=golden_synthetic, ecog=golden_ecog,
+        synthetic=golden_synthetic, ecog=golden_ecog, psd=golden_psd,
     )
     for name, job in jobs.items():
         if not only or name in only:

@@ -366,3 +366,21 @@ def apply_filter_direct(data: np.ndarray, taps: np.ndarray) -> np.ndarray:
     ok = n_in > 0
     out[:, ok] = data[:, ok] - acc[:, ok] / n_in[ok]
     return out
+
+
+def periodogram(data, sampling_freq, n_points, max_freq=None):
+    """``compute_psd`` (src/pyparrm/_utils/_power.py:10-68), restated with ``numpy.fft`` in
+    single precision steps: the first ``n_points`` samples (cropped / zero-padded), bins
+    ``1 .. n_points // 2``, ``float32(|X|)**2 / (fs * n)``, then ``psd[:-1] *= 2`` -- on a
+    2-D array that doubles every row but the last (lines 63-66)."""
+    n_points = int(n_points)
+    freqs = np.abs(np.fft.fftfreq(n_points, 1.0 / sampling_freq)[1:(n_points // 2) + 1])
+    if max_freq is None:
+        max_freq = freqs[-1]
+    last = np.argwhere(freqs <= max_freq)[-1][0]
+    x = np.asarray(data).astype(np.float32)
+    coeffs = np.fft.fft(x, n_points)[..., 1:(n_points // 2) + 1]
+    psd = (1.0 / (sampling_freq * n_points)) * np.abs(coeffs).astype(np.float32) ** 2
+    psd = psd.astype(np.float32)
+    psd[:-1] *= 2
+    return freqs[: last + 1], psd[..., : last + 1]

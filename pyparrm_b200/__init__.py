@@ -44,7 +44,7 @@ def install_as_pyparrm() -> None:
     import importlib
 
     sys.modules.setdefault("pyparrm", sys.modules[__name__])
-    for sub in ("data", "parrm"):
+    for sub in ("data", "parrm", "_utils", "_utils._power"):
         sys.modules.setdefault("pyparrm." + sub, importlib.import_module("." + sub, __name__))
 
 

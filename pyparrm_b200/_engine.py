@@ -24,10 +24,13 @@ from . import _native
 from ._native import check, lib
 
 _CHUNK_BYTES = int(os.environ.get("PYPARRM_B200_CHUNK_MB", "32")) << 20
+# the search prologue reads every row once and writes next to nothing back: bigger chunks,
+# fewer launches (five kernels per chunk), the copy/compute overlap is the same
+_SEARCH_CHUNK_BYTES = int(os.environ.get("PYPARRM_B200_SEARCH_CHUNK_MB", "128")) << 20
 _PINNED_OUT_LIMIT = int(os.environ.get("PYPARRM_B200_PINNED_OUT_MB", "2048")) << 20
 _EVAL_WS_LIMIT = int(os.environ.get("PYPARRM_B200_EVAL_WS_MB", "1024")) << 20
 _N_SLOTS = 3
-_COPY_THREADS = max(1, min(8, (os.cpu_count() or 1)))
+_COPY_THREADS = max(1, min(16, (os.cpu_count() or 1)))
 _copy_pool: ThreadPoolExecutor | None = None
 
 
@@ -38,7 +41,7 @@ def _vp(ptr: int) -> ctypes.c_void_p:
 def _threaded_memmove(dst: int, src: int, nbytes: int) -> None:
     """memcpy between host buffers on several threads (ctypes releases the GIL)."""
     global _copy_pool
-    piece = 8 << 20
+    piece = 4 << 20
     if nbytes <= piece or _COPY_THREADS == 1:
         ctypes.memmove(dst, src, nbytes)
         return
@@ -135,7 +138,8 @@ class DeviceEngine:
         self._stage_out = None
         self._eval_ws = None
         self._plans: dict = {}
-        self.launches = 0          # kernels of ours enqueued (bench.py reports it)
+        self.launches = 0          # launches of ours enqueued: kernels + graph replays
+        self.graph_kernels = 0     # kernels executed inside replayed CUDA graphs
         self.last_filter_kernel = ""
 
     # ------------------------------------------------------------------ helpers
@@ -211,7 +215,7 @@ class DeviceEngine:
                         n_chans=int(n_chans),
                     )
                 )
-            rows = max(1, _CHUNK_BYTES // max(1, n_samples * elem))
+            rows = max(1, _SEARCH_CHUNK_BYTES // max(1, n_samples * elem))
             rows = min(rows, n_chans, 65535)
             in_bytes = rows * n_samples * elem
             slots = self._slots(in_bytes, 16)
@@ -265,8 +269,14 @@ class DeviceEngine:
         y = np.ascontiguousarray(z[:, indices].T, dtype=np.float64)
         with self._lock, t.cuda.device(self.device):
             d_y = t.from_numpy(y).to(self.device)
+            d_sumsq = t.empty(y.shape[1], dtype=t.float64, device=self.device)
+            check(lib.parrm_channel_sumsq(_vp(d_y.data_ptr()), int(y.shape[1]), int(y.shape[1]),
+                                          int(y.shape[0]), _vp(d_sumsq.data_ptr()),
+                                          self._stream_ptr(t.cuda.current_stream())),
+                  "parrm_channel_sumsq")
+            self.launches += 1
             return SearchTile(
-                y=d_y, sumsq=(d_y * d_y).sum(0), indices=t.from_numpy(indices).to(self.device),
+                y=d_y, sumsq=d_sumsq, indices=t.from_numpy(indices).to(self.device),
                 n_indices=int(y.shape[0]), n_chans=int(y.shape[1]),
             )
 
@@ -377,6 +387,91 @@ class DeviceEngine:
                     bandwidth)
             return d_err
 
+    def _eval_into(self, tile, d_per, d_err, bandwidth, lambda_, n_chans_divisor, sp) -> int:
+        """One parrm_eval_periods call on stream ``sp`` (no allocation: capturable); returns
+        the number of kernels it enqueued."""
+        n_periods = int(d_per.shape[0])
+        check(lib.parrm_eval_periods(
+            _vp(tile.y.data_ptr()), tile.n_chans, _vp(tile.sumsq.data_ptr()),
+            _vp(tile.indices.data_ptr()), tile.n_chans, tile.n_indices,
+            _vp(d_per.data_ptr()), n_periods, int(bandwidth), float(lambda_),
+            int(n_chans_divisor), _vp(d_err.data_ptr()),
+            _vp(self._eval_ws.data_ptr()), self._eval_ws.numel(), sp), "parrm_eval_periods")
+        return lib.parrm_eval_launch_count(
+            _vp(tile.y.data_ptr()), tile.n_chans, tile.n_chans, tile.n_indices, n_periods,
+            int(bandwidth))
+
+    ROUNDS_PER_GRAPH = 8
+
+    def nm_minimise(self, tile, starts, bandwidth, lambda_, n_chans_divisor, xtol=1e-4,
+                    ftol=1e-4, maxiter=200, maxfun=200):
+        """``scipy.optimize.fmin`` (defaults) from every entry of ``starts`` on the objective of
+        ``tile``, with the simplex state machines on the device (csrc/neldermead.cu): a round is
+        one batched evaluation of 5 points per chain plus one state-machine step, and
+        ``ROUNDS_PER_GRAPH`` rounds replay as one CUDA graph; the host reads one int32 per
+        replay (chains still running) and the final states.  Returns ``[(x, fval, iterations,
+        fcalls)]`` per chain, as ``fmin(..., full_output=True)[:4]``."""
+        t = self.torch
+        starts = np.ascontiguousarray(starts, dtype=np.float64).ravel()
+        n = int(starts.shape[0])
+        if n == 0:
+            return []
+        bandwidth = int(bandwidth)
+        if bandwidth > _native.MAX_BANDWIDTH:
+            raise ValueError(f"bandwidth {bandwidth} exceeds the device limit {_native.MAX_BANDWIDTH}")
+        with self._lock, t.cuda.device(self.device):
+            need = lib.parrm_eval_workspace_bytes(tile.n_chans, tile.n_indices, 5 * n, bandwidth)
+            if self._eval_ws is None or self._eval_ws.numel() < need:
+                self._eval_ws = self._empty(need, t.uint8)
+            d_starts = t.from_numpy(starts).to(self.device)
+            d_state = t.zeros(n * _native.NM_STATE_BYTES, dtype=t.uint8, device=self.device)
+            d_points = t.empty(5 * n, dtype=t.float64, device=self.device)
+            d_values = t.empty(5 * n, dtype=t.float64, device=self.device)
+            d_active = t.zeros(1, dtype=t.int32, device=self.device)
+            kernels_per_round = [0]
+
+            def one_round(sp):
+                kernels_per_round[0] = 1 + self._eval_into(
+                    tile, d_points, d_values, bandwidth, lambda_, n_chans_divisor, sp)
+                check(lib.parrm_nm_step(
+                    _vp(d_state.data_ptr()), n, _vp(d_values.data_ptr()), _vp(d_points.data_ptr()),
+                    float(xtol), float(ftol), int(maxiter), int(maxfun),
+                    _vp(d_active.data_ptr()), sp), "parrm_nm_step")
+
+            stream = t.cuda.current_stream()
+            sp = self._stream_ptr(stream)
+            check(lib.parrm_nm_init(_vp(d_starts.data_ptr()), n, _vp(d_state.data_ptr()),
+                                    _vp(d_points.data_ptr()), sp), "parrm_nm_init")
+            one_round(sp)  # the initial simplex; also loads every kernel before the capture
+            self.launches += 1 + kernels_per_round[0]
+            active = int(d_active.item())
+            if active:
+                # capture_begin / capture_end directly: torch.cuda.graph() also runs
+                # gc.collect() and empties the allocator cache, tens of ms per capture
+                graph = t.cuda.CUDAGraph()
+                self.s_run.wait_stream(stream)
+                with t.cuda.stream(self.s_run):
+                    graph.capture_begin(capture_error_mode="thread_local")
+                    try:
+                        for _ in range(self.ROUNDS_PER_GRAPH):
+                            one_round(self._stream_ptr(self.s_run))
+                    finally:
+                        graph.capture_end()
+                stream.wait_stream(self.s_run)
+                replays = 0
+                while active and replays * self.ROUNDS_PER_GRAPH < 2 * maxiter + 2:
+                    graph.replay()
+                    replays += 1
+                    active = int(d_active.item())
+                self.launches += replays            # one launch per replay ...
+                self.graph_kernels += replays * self.ROUNDS_PER_GRAPH * kernels_per_round[0]
+            raw = d_state.cpu().numpy().view(np.dtype([
+                ("sim", np.float64, 2), ("fsim", np.float64, 2), ("points", np.float64, 5),
+                ("fcalls", np.int32), ("iterations", np.int32), ("done", np.int32),
+                ("started", np.int32)]))
+            return [(np.float64(r["sim"][0]), np.float64(np.min(r["fsim"])), int(r["iterations"]),
+                     int(r["fcalls"])) for r in raw]
+
     def argmin(self, d_values):
         """(min value, first index) of a device vector, NaNs skipped (on device)."""
         t = self.torch
@@ -407,6 +502,93 @@ class DeviceEngine:
             self.launches += 1
             n = int(d_n.item())
             return d_taps[:n].cpu().numpy()
+
+    # ------------------------------------------------------------ parameter sweeps
+    def default_half_widths(self, periods, period_half_widths, omits, limit: int) -> np.ndarray:
+        """``_get_filter_half_width`` (parrm.py:788-801) for many parameter sets, one launch."""
+        t = self.torch
+        n = len(periods)
+        with self._lock, t.cuda.device(self.device):
+            d_per = t.tensor(np.asarray(periods, dtype=np.float64), device=self.device)
+            d_phw = t.tensor(np.asarray(period_half_widths, dtype=np.float64), device=self.device)
+            d_omit = t.tensor(np.asarray(omits, dtype=np.int64), device=self.device)
+            d_lim = t.full((n,), int(limit), dtype=t.int64, device=self.device)
+            d_out = t.empty(n, dtype=t.int64, device=self.device)
+            check(lib.parrm_default_half_width(
+                _vp(d_per.data_ptr()), _vp(d_phw.data_ptr()), _vp(d_omit.data_ptr()),
+                _vp(d_lim.data_ptr()), n, _vp(d_out.data_ptr()),
+                self._stream_ptr(t.cuda.current_stream())), "parrm_default_half_width")
+            self.launches += 1
+            return d_out.cpu().numpy()
+
+    def filter_sweep(self, data: np.ndarray, periods, period_half_widths, half_widths, omits,
+                     directions):
+        """Filter one recording with many tap sets: ONE tap-building launch and ONE filter
+        launch for the whole sweep (``parrm_build_taps_batch`` -> ``parrm_filter_apply_batch``,
+        the tap lists never leave the device in between).  Returns ``(out, taps)``: float64
+        ``[n_sets, channels, times]`` and the per-set ascending tap offsets (an empty tap set
+        -- the reference's RuntimeError, parrm.py:822-827 -- gives an empty array and zeros)."""
+        t = self.torch
+        data, code = self._as_float_array(data, allow_f32=False)
+        n_sets = len(half_widths)
+        n_chans, n_samples = data.shape
+        max_hw = int(max(half_widths)) if n_sets else 1
+        stride = 2 * max_hw + 1
+        with self._lock, t.cuda.device(self.device):
+            sp = self._stream_ptr(t.cuda.current_stream())
+            dev = lambda a, dt: t.tensor(np.asarray(a, dtype=dt), device=self.device)  # noqa: E731
+            d_per, d_phw = dev(periods, np.float64), dev(period_half_widths, np.float64)
+            d_hw, d_omit = dev(half_widths, np.int64), dev(omits, np.int64)
+            d_dir = dev([_native.DIRECTIONS[d] for d in directions], np.int32)
+            d_taps = t.empty((n_sets, stride), dtype=t.int32, device=self.device)
+            d_n = t.zeros(n_sets, dtype=t.int32, device=self.device)
+            check(lib.parrm_build_taps_batch(
+                _vp(d_per.data_ptr()), _vp(d_phw.data_ptr()), _vp(d_hw.data_ptr()),
+                _vp(d_omit.data_ptr()), _vp(d_dir.data_ptr()), n_sets, _vp(d_taps.data_ptr()),
+                stride, _vp(d_n.data_ptr()), sp), "parrm_build_taps_batch")
+            d_x = t.from_numpy(data).to(self.device)
+            d_out = t.empty((n_sets, n_chans, n_samples), dtype=t.float64, device=self.device)
+            check(lib.parrm_filter_apply_batch(
+                _vp(d_x.data_ptr()), n_samples, n_samples, n_chans, _vp(d_taps.data_ptr()), stride,
+                _vp(d_n.data_ptr()), n_sets, max_hw, _vp(d_out.data_ptr()), n_samples,
+                n_chans * n_samples, code, sp), "parrm_filter_apply_batch")
+            self.launches += 2
+            self.last_filter_kernel = _native.filter_last_kernel()
+            counts = d_n.cpu().numpy()
+            taps_all = d_taps.cpu().numpy()
+            return d_out.cpu().numpy(), [taps_all[i, : counts[i]].copy() for i in range(n_sets)]
+
+    # -------------------------------------------------------------------- power
+    def periodogram(self, data, n_points: int, sampling_freq: float) -> np.ndarray:
+        """Base periodogram of ``compute_psd`` (``_utils/_power.py:63-66``) before its
+        ``psd[:-1] *= 2``: float32 ``[channels, n_points // 2]`` (``[n_points // 2]`` for 1-D
+        input).  ``data``: NumPy array (only the first ``n_points`` samples are uploaded) or a
+        CUDA tensor (float64 / float32, rows contiguous)."""
+        t = self.torch
+        one_d = data.ndim == 1
+        n_bins = int(n_points) // 2
+        with self._lock, t.cuda.device(self.device):
+            if isinstance(data, np.ndarray):
+                head = np.atleast_2d(data)[:, : int(n_points)]
+                head = np.ascontiguousarray(head, dtype=np.float32 if head.dtype != np.float64
+                                            else np.float64)
+                d_x = t.from_numpy(head).to(self.device)
+            else:
+                d_x = data if data.dim() == 2 else data.unsqueeze(0)
+                if d_x.dtype not in (t.float64, t.float32) or d_x.stride(1) != 1:
+                    d_x = d_x.to(t.float64).contiguous()
+            code = _native.F64 if d_x.dtype == t.float64 else _native.F32
+            n_chans, n_samples = d_x.shape
+            d_psd = t.empty((n_chans, n_bins), dtype=t.float32, device=self.device)
+            for c0 in range(0, n_chans, 65535):
+                c1 = min(c0 + 65535, n_chans)
+                check(lib.parrm_periodogram(
+                    _vp(d_x[c0:c1].data_ptr()), c1 - c0, n_samples, d_x.stride(0), code,
+                    int(n_points), float(sampling_freq), _vp(d_psd[c0:c1].data_ptr()), n_bins,
+                    self._stream_ptr(t.cuda.current_stream())), "parrm_periodogram")
+                self.launches += 1
+            psd = d_psd.cpu().numpy()
+        return psd[0] if one_d else psd
 
     # ------------------------------------------------------------------- filter
     def _plan(self, taps: np.ndarray, dtype_code: int, strategy: int | None = None):

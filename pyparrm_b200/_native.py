@@ -19,6 +19,7 @@ F64, F32, I16, I32 = 0, 1, 2, 3
 DIR_BOTH, DIR_PAST, DIR_FUTURE = 0, 1, 2
 DIRECTIONS = {"both": DIR_BOTH, "past": DIR_PAST, "future": DIR_FUTURE}
 MAX_BANDWIDTH = 23
+NM_STATE_BYTES = 88
 ABI_VERSION = 5
 PLAN_AUTO, PLAN_GATHER, PLAN_COMB = 0, 1, 2
 KERNEL_AUTO, KERNEL_GATHER, KERNEL_SPECIALISED = 0, 1, 3
@@ -54,6 +55,7 @@ SIGNATURES = {
         [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_double,
          c_void_p, c_int64, c_void_p, c_int, c_void_p],
     ),
+    "parrm_channel_sumsq": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "parrm_standardise_full": (
         c_int,
         [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_double, c_void_p, c_int64, c_int,
@@ -92,6 +94,25 @@ SIGNATURES = {
     "parrm_convert": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p]),
     "parrm_convert_f64_to_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "parrm_convert_f32_to_f64": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "parrm_nm_init": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "parrm_nm_step": (
+        c_int,
+        [c_void_p, c_int32, c_void_p, c_void_p, c_double, c_double, c_int32, c_int32, c_void_p,
+         c_void_p]),
+    "parrm_default_half_width": (
+        c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "parrm_build_taps_batch": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+         c_void_p]),
+    "parrm_filter_apply_batch": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64,
+         c_void_p, c_int64, c_int64, c_int, c_void_p]),
+    "parrm_periodogram": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_int64, c_int, c_int64, c_double, c_void_p, c_int64, c_void_p],
+    ),
     "parrm_fp64_fma_burn": (c_int, [c_int64, c_void_p, POINTER(c_double), c_void_p]),
 }
 

@@ -8,7 +8,6 @@
 // copy (cp.async.bulk, SASS UBLKCP) and gathers the taps from there.  HBM traffic is the
 // algorithmic 2 * sizeof(T) bytes per channel-sample; the halo re-reads of neighbouring
 // tiles are served by L2.
-#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -158,6 +157,49 @@ filter_gather_global_kernel(const FilterArgs<T> a) {
       }
     }
     orow[t] = n_in > 0 ? finite_or_zero(xrow[t] - acc / T(n_in)) : T(0);
+  }
+}
+
+// ---- batched gather: many tap sets over the same recording in ONE launch ------------
+// The parameter explorer (and any parameter sweep) filters one short recording with many
+// (half-width, period half-width, omit, direction) sets.  blockIdx.z is the set; its taps and
+// tap count are read from device memory (straight from parrm_build_taps_batch, no host round
+// trip); the staged window is sized for the widest set.  Every output counts its in-range
+// taps (the edge form of the kernel above): this path is for small data, not for throughput.
+template <typename T>
+__global__ void __launch_bounds__(kFilterThreads)
+filter_gather_batch_kernel(const T* __restrict__ x, int64_t ld_x, int64_t n_total,
+                           const int32_t* __restrict__ taps, int64_t tap_stride,
+                           const int32_t* __restrict__ n_taps_of, int32_t w_max, int32_t tile,
+                           T* __restrict__ out, int64_t ld_out, int64_t set_stride) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* const s_win = reinterpret_cast<T*>(smem_raw);                    // [tile + 2 w_max]
+  int32_t* const s_taps = reinterpret_cast<int32_t*>(s_win + tile + 2 * w_max);
+  const int64_t set = blockIdx.z, chan = blockIdx.y;
+  const int64_t t_lo = int64_t(blockIdx.x) * tile;
+  const int n_tile = int(min64(tile, n_total - t_lo));
+  const int n_taps = n_taps_of[set];
+  const T* const row = x + chan * ld_x;
+  for (int i = threadIdx.x; i < n_tile + 2 * w_max; i += kFilterThreads) {
+    const int64_t g = t_lo - w_max + i;
+    s_win[i] = (g >= 0 && g < n_total) ? row[g] : T(0);
+  }
+  for (int i = threadIdx.x; i < n_taps; i += kFilterThreads) s_taps[i] = taps[set * tap_stride + i];
+  __syncthreads();
+  T* const orow = out + set * set_stride + chan * ld_out + t_lo;
+  for (int i = threadIdx.x; i < n_tile; i += kFilterThreads) {
+    const int64_t t = t_lo + i;
+    T acc = T(0);
+    int n_in = 0;
+    for (int k = 0; k < n_taps; ++k) {
+      const int w = s_taps[k];
+      const int64_t src = t - w;
+      if (src >= 0 && src < n_total) {
+        acc += s_win[i + w_max - w];
+        ++n_in;
+      }
+    }
+    orow[i] = n_in > 0 ? finite_or_zero(s_win[i + w_max] - acc / T(n_in)) : T(0);
   }
 }
 
@@ -314,6 +356,42 @@ int parrm_filter_apply_ex(const void* d_x, int64_t ld_x, int64_t x_t0, int64_t n
                       d_taps, ld_x, x_t0, n_x, ld_out, t0, n_out, n_samples_total,
                       hdr->n_taps, w_lo, w_hi, 0};
   return launch_filter<float>(a, n_chans, s);
+}
+
+int parrm_filter_apply_batch(const void* d_x, int64_t ld_x, int64_t n_samples, int64_t n_chans,
+                             const int32_t* d_taps, int64_t tap_stride, const int32_t* d_n_taps,
+                             int64_t n_sets, int64_t max_half_width, void* d_out, int64_t ld_out,
+                             int64_t set_stride, int dtype, void* stream) {
+  using namespace parrm;
+  PARRM_REQUIRE(dtype == PARRM_F64 || dtype == PARRM_F32, "parrm_filter_apply_batch: bad dtype %d", dtype);
+  PARRM_REQUIRE(n_sets >= 0 && n_sets <= 65535 && n_chans >= 0 && n_chans <= 65535 && n_samples >= 0,
+                "parrm_filter_apply_batch: bad shape");
+  if (n_sets == 0 || n_chans == 0 || n_samples == 0) return PARRM_OK;
+  PARRM_REQUIRE(d_x && d_taps && d_n_taps && d_out, "parrm_filter_apply_batch: null pointer");
+  const size_t es = dtype == PARRM_F64 ? 8 : 4;
+  PARRM_REQUIRE(max_half_width >= 1 && tap_stride >= 1, "parrm_filter_apply_batch: empty tap rows");
+  const int64_t tile = 2048;
+  const size_t smem = size_t(tile + 2 * max_half_width) * es + size_t(tap_stride) * 4;
+  PARRM_REQUIRE(smem <= size_t(kSmemBudget),
+                "parrm_filter_apply_batch: half-width %lld too wide for the batched kernel "
+                "(filter the sets one by one with parrm_filter_apply)", (long long)max_half_width);
+  dim3 grid(unsigned(ceil_div(n_samples, tile)), unsigned(n_chans), unsigned(n_sets));
+  if (dtype == PARRM_F64) {
+    auto kernel = filter_gather_batch_kernel<double>;
+    PARRM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    kernel<<<grid, kFilterThreads, smem, as_stream(stream)>>>(
+        static_cast<const double*>(d_x), ld_x, n_samples, d_taps, tap_stride, d_n_taps,
+        int32_t(max_half_width), int32_t(tile), static_cast<double*>(d_out), ld_out, set_stride);
+  } else {
+    auto kernel = filter_gather_batch_kernel<float>;
+    PARRM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    kernel<<<grid, kFilterThreads, smem, as_stream(stream)>>>(
+        static_cast<const float*>(d_x), ld_x, n_samples, d_taps, tap_stride, d_n_taps,
+        int32_t(max_half_width), int32_t(tile), static_cast<float*>(d_out), ld_out, set_stride);
+  }
+  PARRM_LAUNCH_OK("filter_gather_batch_kernel");
+  g_last_kernel = "filter_gather_batch_kernel";
+  return PARRM_OK;
 }
 
 }  // extern "C"

@@ -23,28 +23,17 @@
 // candidates, e.g. Nelder-Mead steps); partials are combined in a fixed order.
 // Kernel 2 (solve) assembles the Gram matrix, factorises it with partial pivoting (zero pivot
 // -> +inf, the reference's LinAlgError path), solves all channels and reduces the objective.
-#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace parrm {
 
-constexpr int kAccThreads = 256;
-constexpr int kSuper = 256;       // samples per sincos batch (one per thread)
 constexpr int kSplitQuantum = 512;  // sample splits are multiples of every kernel's batch
-constexpr int kKT = 64;           // samples per GEMM tile
-constexpr int kGroups = 4;        // harmonic groups per sample (kGroups * kKT == kAccThreads)
-constexpr int kHMax = (2 * PARRM_MAX_BANDWIDTH + kGroups - 1) / kGroups;  // 12
+constexpr int kKT = 64;           // narrow kernel: samples per sub-batch
 constexpr int kMaxRows = 2 * PARRM_MAX_BANDWIDTH + 1;                     // 47
-constexpr int kRowsPad = 48;      // padded design-matrix row: 8 row groups x 6
-constexpr int kRowStride = 50;    // smem stride of a sample's row (doubles): 16-byte aligned
-                                  // for LDS.128 and 100 words = 4 banks/lane, so the per-sample
-                                  // stores of the generator are 2-way instead of 32-way conflicted
-constexpr int kRowTile = 6;
+constexpr int kRowsPad = 48;      // padded design-matrix rows: six 8-row blocks
 static_assert(kMaxRows <= kRowsPad, "row groups must cover the widest design matrix");
-constexpr int kColTile = 4;
 constexpr int kChanTile = 64;     // channels per CTA (16 column groups x 4)
-constexpr int kHalf = 128;        // threads per K-half
 
 struct EvalShape {
   int64_t n_chans, n_indices, n_periods;
@@ -150,178 +139,6 @@ __device__ __forceinline__ void cp_async_commit() {
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-__global__ void __launch_bounds__(kAccThreads, 2)
-eval_accumulate_kernel(const double* __restrict__ y, const int64_t* __restrict__ indices,
-                       const double* __restrict__ periods, double* __restrict__ ws,
-                       const EvalShape sh) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2* s_cs = reinterpret_cast<double2*>(smem_raw);                 // [kSuper] (cos, sin)
-  double* s_w = reinterpret_cast<double*>(smem_raw + kSuper * 16);      // [kKT][kRowStride]
-  double* s_y = s_w + kKT * kRowStride;      // 2 x [kKT][2 planes][16 column groups][2], see y_slot
-  double* s_red = s_y + 2 * kKT * kChanTile;                            // [8 warps][2*H]
-  constexpr int H = kHMax;
-
-  const int tid = threadIdx.x;
-  const int64_t cand = blockIdx.x;
-  const int split = blockIdx.y;
-  const int ctile = blockIdx.z;
-  const int bw = sh.bandwidth, two_bw = 2 * bw;
-  const int n_rows = sh.n_rows;
-  const int64_t n_begin = int64_t(split) * sh.split_len;
-  const int64_t n_end = min(n_begin + sh.split_len, sh.n_indices);
-  const int chan0 = ctile * kChanTile;
-  const int n_chan_here = int(min64(kChanTile, sh.n_chans - chan0));
-  const double delta = 6.283185307179586 / periods[cand];  // 2*pi/period (parrm.py:619)
-
-  // generator role: sample lane gi, harmonic group gg -> harmonics gg*h+1 .. gg*h+h
-  const int gi = tid & (kKT - 1), gg = tid / kKT;
-  const int h = (two_bw + kGroups - 1) / kGroups;
-  const int m0 = gg * h;
-  double sum_c[H], sum_s[H];
-#pragma unroll
-  for (int j = 0; j < H; ++j) sum_c[j] = sum_s[j] = 0.0;
-
-  // GEMM role: K-half kh, row group rg (6 rows), column group cg (4 channels)
-  const int kh = tid / kHalf, th = tid % kHalf;
-  const int rg = th / 16, cg = th % 16;
-  const bool rows_live = rg * kRowTile < n_rows;
-  double acc[kRowTile][kColTile];
-#pragma unroll
-  for (int r = 0; r < kRowTile; ++r)
-#pragma unroll
-    for (int c = 0; c < kColTile; ++c) acc[r][c] = 0.0;
-
-  // Y tiles (sample-major rows of the standardised data) stream through two shared-memory
-  // buffers with cp.async, one tile ahead of the GEMM, so their global-memory latency is
-  // hidden behind the harmonic generation and the FMA tiles.
-  auto stage_y = [&](int buf, int64_t n_tile) {
-    double* dst = s_y + buf * (kKT * kChanTile);
-    for (int e = tid; e < kKT * kChanTile; e += kAccThreads) {
-      const int k = e / kChanTile, c = e % kChanTile;
-      const int64_t n = n_tile + k;
-      const bool ok = n < n_end && c < n_chan_here;
-      cp_async8(dst + y_slot(k, c), ok ? y + n * sh.ld_y + chan0 + c : y, ok ? 8 : 0);
-    }
-    cp_async_commit();
-  };
-  int y_buf = 0;
-  if (n_begin < n_end) stage_y(0, n_begin);
-
-  for (int64_t n_super = n_begin; n_super < n_end; n_super += kSuper) {
-    // one accurate sincos per sample of this batch; invalid lanes hold (0, 0)
-    {
-      const int64_t n = n_super + tid;
-      double2 cs = make_double2(0.0, 0.0);
-      if (n < n_end) {
-        const double angle = double(indices[n] + 1) * delta;
-        sincos_phase(angle, &cs.y, &cs.x);
-      }
-      s_cs[tid] = cs;
-    }
-    __syncthreads();
-    for (int sub = 0; sub < kSuper / kKT; ++sub) {
-      const int64_t n_tile = n_super + sub * kKT;
-      if (n_tile >= n_end) break;  // uniform
-      // ---- generate harmonics of kKT samples ----
-      {
-        const int64_t n = n_tile + gi;
-        const bool live = n < n_end;
-        const double2 cs1 = s_cs[sub * kKT + gi];
-        double c, s;
-        cpow(cs1.x, cs1.y, m0, c, s);
-        double* wrow = s_w + gi * kRowStride;
-        if (gg == 0) wrow[0] = live ? 1.0 : 0.0;
-#pragma unroll
-        for (int j = 0; j < H; ++j) {
-          if (j >= h) break;  // uniform
-          cmul(c, s, cs1.x, cs1.y);
-          const int m = m0 + j + 1;
-          if (m <= two_bw && live) {
-            sum_c[j] += c;
-            sum_s[j] += s;
-          }
-          if (m <= bw) {  // columns 2m-1 = sin, 2m = cos (parrm.py:622-623)
-            wrow[2 * m - 1] = live ? s : 0.0;
-            wrow[2 * m] = live ? c : 0.0;
-          }
-        }
-        // zero the padding rows once per tile so the FMA tiles can run unmasked
-        if (gg == kGroups - 1)
-          for (int r = n_rows; r < kRowsPad; ++r) wrow[r] = 0.0;
-      }
-      // ---- this tile's Y has been in flight since the previous tile; start the next one ----
-      if (n_tile + kKT < n_end) {
-        stage_y(y_buf ^ 1, n_tile + kKT);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
-      __syncthreads();
-      // ---- B += W' Y over this K-half's 32 samples ----
-      if (rows_live) {
-        const double* wp = s_w + (kh * (kKT / 2)) * kRowStride + rg * kRowTile;
-        const double* yp = s_y + y_buf * (kKT * kChanTile) + (kh * (kKT / 2)) * kChanTile + cg * 2;
-#pragma unroll 4
-        for (int k = 0; k < kKT / 2; ++k) {
-          const double2 w01 = *reinterpret_cast<const double2*>(wp + k * kRowStride);
-          const double2 w23 = *reinterpret_cast<const double2*>(wp + k * kRowStride + 2);
-          const double2 w45 = *reinterpret_cast<const double2*>(wp + k * kRowStride + 4);
-          const double2 y01 = *reinterpret_cast<const double2*>(yp + k * kChanTile);
-          const double2 y23 = *reinterpret_cast<const double2*>(yp + k * kChanTile + kChanTile / 2);
-          const double wv[kRowTile] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y};
-          const double yv[kColTile] = {y01.x, y01.y, y23.x, y23.y};
-#pragma unroll
-          for (int r = 0; r < kRowTile; ++r)
-#pragma unroll
-            for (int c = 0; c < kColTile; ++c) acc[r][c] = fma(wv[r], yv[c], acc[r][c]);
-        }
-      }
-      __syncthreads();
-      y_buf ^= 1;
-    }
-  }
-
-  // ---- write the B partial of this (candidate, split, K-half) ----
-  {
-    double* bp = ws + cand * sh.b_stride_period + (int64_t(split) * 2 + kh) * sh.b_stride_split;
-#pragma unroll
-    for (int r = 0; r < kRowTile; ++r) {
-      const int row = rg * kRowTile + r;
-      if (row < n_rows) {
-#pragma unroll
-        for (int c = 0; c < kColTile; ++c) {
-          const int ch = cg * kColTile + c;
-          if (ch < n_chan_here) bp[int64_t(row) * sh.n_chans + chan0 + ch] = acc[r][c];
-        }
-      }
-    }
-  }
-  // ---- harmonic sums: reduce the kKT sample lanes of each group (channel tile 0 only) ----
-  if (ctile == 0) {
-    const int warp = tid >> 5, lane = tid & 31;
-#pragma unroll
-    for (int j = 0; j < H; ++j) {
-      const double c = warp_sum(sum_c[j]);
-      const double s = warp_sum(sum_s[j]);
-      if (lane == 0) {
-        s_red[warp * 2 * H + j] = c;
-        s_red[warp * 2 * H + H + j] = s;
-      }
-    }
-    __syncthreads();
-    // kKT/32 = 2 warps per group: warps 2g and 2g+1
-    double* tp = ws + sh.t_offset + cand * sh.t_stride_period + int64_t(split) * sh.t_stride_split;
-    for (int e = tid; e < kGroups * H; e += kAccThreads) {
-      const int g = e / H, j = e % H;
-      const int m = g * h + j + 1;
-      if (j < h && m <= two_bw) {
-        tp[m - 1] = s_red[(2 * g) * 2 * H + j] + s_red[(2 * g + 1) * 2 * H + j];
-        tp[two_bw + m - 1] = s_red[(2 * g) * 2 * H + H + j] + s_red[(2 * g + 1) * 2 * H + H + j];
-      }
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1276,9 +1093,7 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
   cudaStream_t s = as_stream(stream);
   double* ws = static_cast<double*>(d_workspace);
   dim3 grid((unsigned)n_periods, (unsigned)sh.n_splits, (unsigned)sh.n_chan_tiles);
-  const char* two_phase = getenv("PARRM_EVAL_TWO_PHASE");
-  const char* no_narrow = getenv("PARRM_EVAL_NO_NARROW");
-  if (n_chans <= 2 && !(no_narrow && *no_narrow == '1')) {
+  if (n_chans <= 2) {
     dim3 narrow_grid((unsigned)n_periods, (unsigned)sh.n_splits, 1);
     if (n_chans == 1)
       eval_accumulate_narrow_kernel<1><<<narrow_grid, kNarrowThreads, 0, s>>>(d_y, d_indices,
@@ -1286,12 +1101,6 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
     else
       eval_accumulate_narrow_kernel<2><<<narrow_grid, kNarrowThreads, 0, s>>>(d_y, d_indices,
                                                                               d_periods, ws, sh);
-  } else if (two_phase && *two_phase == '1') {  // scalar-FMA form, kept as an A/B baseline
-    const size_t smem = size_t(kSuper * 16 + (kKT * kRowStride + 2 * kKT * kChanTile + 8 * 2 * kHMax) *
-                                                 sizeof(double));
-    PARRM_CUDA_OK(cudaFuncSetAttribute(eval_accumulate_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    eval_accumulate_kernel<<<grid, kAccThreads, smem, s>>>(d_y, d_indices, d_periods, ws, sh);
   } else {
     sh.row0_from_colsum = 1;
     eval_colsum_kernel<<<dim3(unsigned(ceil_div(n_chans, 32)), kColsumBlocks), dim3(32, 32), 0, s>>>(

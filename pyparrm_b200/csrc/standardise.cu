@@ -202,3 +202,17 @@ int parrm_standardise_full(const void* d_x, int64_t n_chans, int64_t n_samples, 
 }
 
 }  // extern "C"
+
+// sum_j y[j, c]^2 of a sample-major tile (the y'y term of the evaluator's quadratic form) for
+// callers that bring an already standardised tile (PARRM._optimise_local's seam).
+extern "C" int parrm_channel_sumsq(const double* d_y, int64_t ld_y, int64_t n_chans,
+                                   int64_t n_indices, double* d_sumsq, void* stream) {
+  PARRM_REQUIRE(n_chans >= 0 && n_chans <= 65535 && n_indices >= 0 && ld_y >= n_chans,
+                "parrm_channel_sumsq: bad shape");
+  if (n_chans == 0) return PARRM_OK;
+  PARRM_REQUIRE(d_y != nullptr && d_sumsq != nullptr, "parrm_channel_sumsq: null pointer");
+  parrm::channel_sumsq_kernel<<<unsigned(n_chans), 256, 0, parrm::as_stream(stream)>>>(
+      d_y, ld_y, n_indices, d_sumsq);
+  PARRM_LAUNCH_OK("channel_sumsq_kernel");
+  return PARRM_OK;
+}

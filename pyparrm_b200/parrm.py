@@ -332,6 +332,16 @@ class PARRM:
             )
         return self._evaluate(periods, tile, bandwidth, lambda_)
 
+    def _fmin(self, starts, tile, bandwidth, lambda_):
+        """``scipy.optimize.fmin`` at its defaults from each start (parrm.py:499-517, 545-550):
+        on the device engine the simplex state machines run on the GPU with the rounds replayed
+        as CUDA graphs (``DeviceEngine.nm_minimise``); any other engine drives the same state
+        machines from the host (``_neldermead.fmin_batch``)."""
+        engine = _engine.get_engine()
+        if hasattr(engine, "nm_minimise"):
+            return engine.nm_minimise(tile, starts, bandwidth, lambda_, self._n_chans)
+        return fmin_batch(lambda p: self._evaluate(p, tile, bandwidth, lambda_), starts)
+
     def _optimise_period_estimate_first_run(self, periods, tile, bandwidth, lambda_):
         """Evaluate the grid and rank it (reference parrm.py:407-465)."""
         fit_error = self._evaluate_grid(periods, tile, bandwidth, lambda_)
@@ -345,9 +355,7 @@ class PARRM:
     def _optimise_period_estimate_second_run(self, periods, fit_errors, tile, bandwidth, lambda_):
         """Nelder-Mead from the best five candidates (reference parrm.py:467-522)."""
         n_iters = int(np.min((_N_RESTARTS, periods.shape[0])))
-        results = fmin_batch(
-            lambda p: self._evaluate(p, tile, bandwidth, lambda_), periods[:n_iters]
-        )
+        results = self._fmin(periods[:n_iters], tile, bandwidth, lambda_)
         for k, (x, fval, _, _) in enumerate(results):
             periods[k] = x
             fit_errors[k] = fval
@@ -355,7 +363,7 @@ class PARRM:
 
     def _optimise_period_estimate_final_run(self, period, tile, bandwidth):
         """Unregularised polish of the final estimate (reference parrm.py:524-550)."""
-        return fmin_batch(lambda p: self._evaluate(p, tile, bandwidth, 0.0), [period])[0][0]
+        return self._fmin([period], tile, bandwidth, 0.0)[0][0]
 
     def _optimise_local(self, period, data, indices, bandwidth, lambda_) -> float:
         """Fit error for one period (the reference's evaluator seam, parrm.py:552-597).
@@ -525,6 +533,61 @@ class PARRM:
         if self._verbose:
             print("    ... Data filtered\n")
         return self._filtered_data
+
+    def filter_sweep(self, parameter_sets, data=None):
+        """Filter with many parameter sets at once (additive).
+
+        ``parameter_sets``: iterable of dicts with the keyword arguments of
+        :meth:`create_filter` (``filter_half_width``, ``omit_n_samples``, ``filter_direction``,
+        ``period_half_width``; missing keys take ``create_filter``'s defaults, validated with
+        the same rules and messages).  The default half-widths of all sets come from one
+        launch, all tap sets from one launch and all filtered copies from one launch -- what
+        the reference's explorer does with one ``_generate_filter`` + ``filter_data`` per
+        widget event (``_utils/_plotting.py:568-584``).  Returns ``(filtered, taps)``:
+        float64 ``[n_sets, channels, times]`` and the list of tap-offset arrays.  Leaves the
+        object's own filter untouched."""
+        if self._period is None:
+            raise ValueError(_PERIOD_FIRST_MSG)
+        data = self._check_sort_filter_data_inputs(data)
+        engine = _engine.get_engine()
+        half_span = (self._n_samples - 1) // 2
+        sets = [dict(s) for s in parameter_sets]
+        omits, phws, hws, dirs = [], [], [], []
+        for s in sets:
+            omit = s.get("omit_n_samples", 0)
+            if not isinstance(omit, int):
+                raise TypeError("`omit_n_samples` must be an int.")
+            if omit < 0 or omit >= half_span:
+                raise ValueError(
+                    "`omit_n_samples` must lie in the range [0, (no. of samples - 1) // 2).")
+            phw = s.get("period_half_width")
+            if phw is None:
+                phw = self._period / 50
+            _require_number(phw, "period_half_width")
+            if phw <= 0 or phw > self._period:
+                raise ValueError("`period_half_width` must be lie in the range (0, period].")
+            direction = s.get("filter_direction", "both")
+            if not isinstance(direction, str):
+                raise TypeError("`filter_direction` must be a str.")
+            if direction not in _DIRECTIONS:
+                raise ValueError(f"`filter_direction` must be one of {_DIRECTIONS}.")
+            omits.append(omit), phws.append(float(phw)), dirs.append(direction)
+            hws.append(s.get("filter_half_width"))
+        missing = [i for i, hw in enumerate(hws) if hw is None]
+        if missing:  # parrm.py:788-801 for every set that asked for the default, one launch
+            found = engine.default_half_widths(
+                [self._period] * len(missing), [phws[i] for i in missing],
+                [omits[i] for i in missing], half_span)
+            for i, hw in zip(missing, found):
+                hws[i] = int(hw)
+        for hw, omit in zip(hws, omits):
+            if not isinstance(hw, int):
+                raise TypeError("`filter_half_width` must be an int.")
+            if hw <= omit or hw > half_span:
+                raise ValueError(
+                    "`filter_half_width` must lie in the range (`omit_n_samples`, "
+                    "(no. of samples - 1) // 2].")
+        return engine.filter_sweep(data, [float(self._period)] * len(sets), phws, hws, omits, dirs)
 
     def _check_sort_filter_data_inputs(self, data) -> np.ndarray:
         """Reference parrm.py:877-886."""

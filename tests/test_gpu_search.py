@@ -239,3 +239,34 @@ def test_large_sample_indices(gpu_engine):
         got = gpu_engine.evaluate(tile, periods, 20, 1.0, n_chans)
         want = oracle.objective_many(periods, z, idx, 20, 1.0, n_chans, n_jobs=4)
         compare_objective(got, want, "large indices", periods, idx, 20)
+
+
+def test_device_nelder_mead_retraces_host_state_machines(gpu_engine):
+    """csrc/neldermead.cu vs pyparrm_b200/_neldermead.py (itself pinned to scipy.optimize.fmin
+    by tests/test_neldermead.py): x, fval, nit and nfev of every chain bit-equal, when both
+    see the same objective values (same evaluator, same batch shape of 5 points per chain)."""
+    from pyparrm_b200._neldermead import fmin_batch
+
+    data = make_recording(3, 40_000, 2000, 130, seed=12)
+    z = oracle.standardise(data, 3.0)
+    for idx, bw, lam, starts in (
+        (np.arange(5_000, 10_001), 5, 1.0, [15.38, 15.3846, 15.40, 15.2, 15.39]),
+        (np.arange(2_000, 27_001), 20, 0.0, [2000 / 130]),
+        (np.arange(100, 1_100), 10, 1.0, [7.7, 15.5]),
+    ):
+        tile = gpu_engine.tile_from_standardised(z, idx)
+        n = len(starts)
+
+        def evaluate(p, tile=tile, n=n, bw=bw, lam=lam):
+            padded = np.resize(np.asarray(p, dtype=np.float64), 5 * n)  # same launch shape
+            return gpu_engine.evaluate(tile, padded, bw, lam, 3)[: len(p)]
+
+        want = fmin_batch(evaluate, starts)
+        launches0 = gpu_engine.launches
+        got = gpu_engine.nm_minimise(tile, starts, bw, lam, 3)
+        rounds = max(w[2] for w in want)
+        # init + first round eagerly (<= 7 kernels), then one launch per replayed graph
+        assert gpu_engine.launches - launches0 <= 8 + rounds // gpu_engine.ROUNDS_PER_GRAPH + 1
+        for g, w in zip(got, want):
+            assert g[0] == w[0] and (g[1] == w[1] or (np.isnan(g[1]) and np.isnan(w[1])))
+            assert g[2:] == (w[2], w[3]), (g, w)

@@ -151,3 +151,15 @@ def test_find_period_end_to_end(golden, name):
         np.testing.assert_array_equal(taps, g[f"{direction}_taps"])
         filt = oracle.build_filter(period, period / 50, hw, 0, direction)
         np.testing.assert_array_equal(oracle.apply_filter_fft(data, filt), g[f"{direction}_filtered"])
+
+
+def test_periodogram_matches_reference_compute_psd(golden):
+    """oracle.periodogram vs the reference's compute_psd outputs (tests/golden/psd.npz)."""
+    g = golden("psd")
+    for k in range(int(g["n_cases"])):
+        fs, n, fmax = g[f"case{k}_args"]
+        freqs, psd = oracle.periodogram(g[f"case{k}_x"], fs, int(n), None if fmax < 0 else fmax)
+        want = g[f"case{k}_psd"]
+        assert np.array_equal(freqs, g[f"case{k}_freqs"])
+        assert psd.dtype == np.float32 and psd.shape == want.shape
+        assert np.abs(psd - want).max() <= 1e-5 * np.abs(want).max()
