@@ -386,6 +386,8 @@ def run_b200(args):
         dev_seconds = max_over_ranks(dist, start.elapsed_time(stop) * 1e-3)
         kernel_seconds = start.elapsed_time(stop) * 1e-3 / args.steps  # one launch per step
 
+        standardise = bench_standardise(engine, d_x, hbm_peak) if world == 1 else None
+
         # ---- e2e: public API, host in / host out (sharded through enable_sharding) ---
         for _ in range(min(args.warmup, 3)):
             parrm.filter_data()
@@ -461,6 +463,8 @@ def run_b200(args):
         "find_period": search,
         "strong": strong,
     }
+    if standardise is not None:
+        line["standardise"] = standardise
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if variants:
@@ -471,6 +475,45 @@ def run_b200(args):
     if dist is not None:
         disable_sharding()
         dist.destroy_process_group()
+
+
+def bench_standardise(engine, d_x, hbm_peak):
+    """Row a1 (_standardise_data, parrm.py:272-280) on the device-resident recording: the
+    streaming mean|diff| reduction reads every sample once (8 B per channel-sample)."""
+    import torch
+
+    from pyparrm_b200 import _native
+    from pyparrm_b200._engine import _vp
+
+    n_chans, n_samples = d_x.shape
+    lib = _native.lib
+    ws_bytes = lib.parrm_channel_scales_workspace_bytes(n_chans, n_samples)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device="cuda")
+    scale = torch.empty(n_chans, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream()
+    sp = _vp(stream.cuda_stream)
+
+    def once():
+        _native.check(lib.parrm_channel_scales(_vp(d_x.data_ptr()), n_chans, n_samples, n_samples,
+                                               _vp(scale.data_ptr()), _vp(ws.data_ptr()), ws_bytes,
+                                               _native.F64, sp), "parrm_channel_scales")
+
+    for _ in range(3):
+        once()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record(stream)
+    for _ in range(reps):
+        once()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    seconds = e0.elapsed_time(e1) * 1e-3 / reps
+    achieved = 8.0 * n_chans * n_samples / seconds / 1e9
+    return {"kernel": "abs_diff_partial_kernel + scale_finalise_kernel (parrm_channel_scales)",
+            "ms": 1e3 * seconds, "value": n_chans * n_samples / seconds, "unit": "channel-samples/s",
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak,
+                         "algorithmic_bytes_per_launch": 8.0 * n_chans * n_samples}}
 
 
 def bench_e2e_variants(engine, data, taps, steps, period):

@@ -96,8 +96,8 @@ int parrm_standardise_gather(const void* d_x, int64_t n_chans, int64_t n_samples
                              int dtype, void* stream);
 /* d_sumsq[c] = sum_j d_y[j * ld_y + c]^2 for a tile the caller standardised itself (the
  * `_optimise_local(period, data, indices, ...)` seam, parrm.py:552-559). */
-int parrm_channel_sumsq(const double* d_y, int64_t ld_y, int64_t n_chans, int64_t n_indices,
-                        double* d_sumsq, void* stream);
+int parrm_channel_sumsq(const void* d_y, int y_dtype, int64_t ld_y, int64_t n_chans,
+                        int64_t n_indices, double* d_sumsq, void* stream);
 /* Full z[c, 0..n_samples-2] (the `_standard_data` attribute), same dtype as x. */
 int parrm_standardise_full(const void* d_x, int64_t n_chans, int64_t n_samples, int64_t ld,
                            const double* d_scale, double outlier_boundary,
@@ -126,6 +126,23 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
                        int bandwidth, double lambda, int64_t n_chans_divisor,
                        double* d_fit_error,
                        void* d_workspace, size_t workspace_bytes, void* stream);
+/* The same with the tile's storage type given: y_dtype = PARRM_F64 (as above) or PARRM_F32,
+ * the search's "fp32" mode (SURVEY 8(b) proposed `dtype` here; BASELINE north_star: period
+ * within 1e-4).  Policy: float32 STORAGE of the standardised tile -- what is resident in L2,
+ * what parrm_standardise_gather's consumers keep and what the sharded search all-gathers --
+ * widened once per call; the fit itself stays on the FP64 tensor path (DMMA).  An FP32
+ * CUDA-core accumulate was rejected on measurement grounds: B200's FP32 FMA peak is only 2x
+ * its DMMA rate, a register-tiled FFMA GEMM of this shape (40 x 64 x N) reaches well under
+ * half of it, and sums over 25 000 samples in float32 cost the objective ~1e-4 of its value;
+ * TF32 tensor cores (10-bit mantissa) are not used anywhere. */
+size_t parrm_eval_workspace_bytes_typed(int64_t n_chans, int64_t n_indices, int64_t n_periods,
+                                        int bandwidth, int y_dtype);
+int parrm_eval_periods_typed(const void* d_y, int y_dtype, int64_t ld_y, const double* d_sumsq,
+                             const int64_t* d_indices, int64_t n_chans, int64_t n_indices,
+                             const double* d_periods, int64_t n_periods,
+                             int bandwidth, double lambda, int64_t n_chans_divisor,
+                             double* d_fit_error,
+                             void* d_workspace, size_t workspace_bytes, void* stream);
 /* First index of the smallest non-NaN value (NaN entries are skipped; all-NaN -> index 0). */
 int parrm_argmin(const double* d_values, int64_t n, double* d_min_value, int64_t* d_min_index,
                  void* stream);

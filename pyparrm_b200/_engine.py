@@ -30,7 +30,7 @@ _SEARCH_CHUNK_BYTES = int(os.environ.get("PYPARRM_B200_SEARCH_CHUNK_MB", "128"))
 _PINNED_OUT_LIMIT = int(os.environ.get("PYPARRM_B200_PINNED_OUT_MB", "2048")) << 20
 _EVAL_WS_LIMIT = int(os.environ.get("PYPARRM_B200_EVAL_WS_MB", "1024")) << 20
 _N_SLOTS = 3
-_COPY_THREADS = max(1, min(16, (os.cpu_count() or 1)))
+_COPY_THREADS = max(1, min(8, (os.cpu_count() or 1)))
 _copy_pool: ThreadPoolExecutor | None = None
 
 
@@ -41,7 +41,7 @@ def _vp(ptr: int) -> ctypes.c_void_p:
 def _threaded_memmove(dst: int, src: int, nbytes: int) -> None:
     """memcpy between host buffers on several threads (ctypes releases the GIL)."""
     global _copy_pool
-    piece = 4 << 20
+    piece = 8 << 20
     if nbytes <= piece or _COPY_THREADS == 1:
         ctypes.memmove(dst, src, nbytes)
         return
@@ -107,11 +107,17 @@ class pin_array:
 class SearchTile:
     """Standardised samples of one search run, resident on the device."""
 
-    y: object          # torch [n_indices, n_chans] float64, sample-major
+    y: object          # torch [n_indices, n_chans] float64 (float32 in the fp32 mode), sample-major
     sumsq: object      # torch [n_chans] float64
     indices: object    # torch [n_indices] int64
     n_indices: int
     n_chans: int
+
+    @property
+    def y_code(self) -> int:
+        import torch
+
+        return _native.F32 if self.y.dtype == torch.float32 else _native.F64
 
 
 class DeviceEngine:
@@ -188,7 +194,8 @@ class DeviceEngine:
 
     # ------------------------------------------------------------- period search
     def prepare_tiles(
-        self, data: np.ndarray, index_sets: list[np.ndarray], outlier_boundary: float
+        self, data: np.ndarray, index_sets: list[np.ndarray], outlier_boundary: float,
+        precision: str = "fp64",
     ) -> list[SearchTile]:
         """Stream the recording through the device once: per-channel scale + gather.
 
@@ -257,6 +264,14 @@ class DeviceEngine:
                     self.launches += 2
                 slot["ev_run"].record(self.s_run)
                 slot["used"] = True
+            if precision == "fp32":  # float32 storage of the tiles; sums of the rounded values
+                with t.cuda.stream(self.s_run):
+                    for tile in tiles:
+                        tile.y = tile.y.to(t.float32)
+                        check(lib.parrm_channel_sumsq(
+                            _vp(tile.y.data_ptr()), _native.F32, tile.n_chans, tile.n_chans,
+                            tile.n_indices, _vp(tile.sumsq.data_ptr()), run), "parrm_channel_sumsq")
+                        self.launches += 1
             self.s_run.synchronize()
             self._scale = scale
             return tiles
@@ -270,8 +285,8 @@ class DeviceEngine:
         with self._lock, t.cuda.device(self.device):
             d_y = t.from_numpy(y).to(self.device)
             d_sumsq = t.empty(y.shape[1], dtype=t.float64, device=self.device)
-            check(lib.parrm_channel_sumsq(_vp(d_y.data_ptr()), int(y.shape[1]), int(y.shape[1]),
-                                          int(y.shape[0]), _vp(d_sumsq.data_ptr()),
+            check(lib.parrm_channel_sumsq(_vp(d_y.data_ptr()), _native.F64, int(y.shape[1]),
+                                          int(y.shape[1]), int(y.shape[0]), _vp(d_sumsq.data_ptr()),
                                           self._stream_ptr(t.cuda.current_stream())),
                   "parrm_channel_sumsq")
             self.launches += 1
@@ -287,7 +302,7 @@ class DeviceEngine:
         the sample-major ``[samples, channels]`` layout."""
         t = self.torch
         with self._lock, t.cuda.device(self.device):
-            y = t.zeros((tile.n_indices, per), dtype=t.float64, device=self.device)
+            y = t.zeros((tile.n_indices, per), dtype=tile.y.dtype, device=self.device)
             y[:, : tile.n_chans] = tile.y
             sumsq = t.zeros(per, dtype=t.float64, device=self.device)
             sumsq[: tile.n_chans] = tile.sumsq
@@ -359,12 +374,13 @@ class DeviceEngine:
             d_err = t.empty(n_periods, dtype=t.float64, device=self.device)
             # One launch for the whole grid when its workspace fits (the sample splits, and with
             # them the workspace per candidate, shrink as the batch grows); otherwise halve.
+            code = tile.y_code
             batch = n_periods
-            while batch > 1 and lib.parrm_eval_workspace_bytes(
-                    tile.n_chans, tile.n_indices, batch, bandwidth) > _EVAL_WS_LIMIT:
+            while batch > 1 and lib.parrm_eval_workspace_bytes_typed(
+                    tile.n_chans, tile.n_indices, batch, bandwidth, code) > _EVAL_WS_LIMIT:
                 batch = -(-batch // 2)
             ws_bytes = max(
-                lib.parrm_eval_workspace_bytes(tile.n_chans, tile.n_indices, b, bandwidth)
+                lib.parrm_eval_workspace_bytes_typed(tile.n_chans, tile.n_indices, b, bandwidth, code)
                 for b in {batch, n_periods % batch or batch}
             )
             if self._eval_ws is None or self._eval_ws.numel() < ws_bytes:
@@ -372,31 +388,28 @@ class DeviceEngine:
             sp = self._stream_ptr(t.cuda.current_stream())
             for p0 in range(0, n_periods, batch):
                 p1 = min(p0 + batch, n_periods)
-                need = lib.parrm_eval_workspace_bytes(tile.n_chans, tile.n_indices, p1 - p0, bandwidth)
+                need = lib.parrm_eval_workspace_bytes_typed(tile.n_chans, tile.n_indices, p1 - p0,
+                                                            bandwidth, code)
                 if self._eval_ws.numel() < need:
                     self._eval_ws = self._empty(need, t.uint8)
-                check(lib.parrm_eval_periods(
-                    _vp(tile.y.data_ptr()), tile.n_chans, _vp(tile.sumsq.data_ptr()),
-                    _vp(tile.indices.data_ptr()), tile.n_chans, tile.n_indices,
-                    _vp(d_per.data_ptr() + 8 * p0), p1 - p0, bandwidth, float(lambda_),
-                    int(n_chans_divisor), _vp(d_err.data_ptr() + 8 * p0),
-                    _vp(self._eval_ws.data_ptr()), self._eval_ws.numel(), sp),
-                    "parrm_eval_periods")
-                self.launches += lib.parrm_eval_launch_count(
-                    _vp(tile.y.data_ptr()), tile.n_chans, tile.n_chans, tile.n_indices, p1 - p0,
-                    bandwidth)
+                self.launches += self._eval_into(tile, d_per[p0:p1], d_err[p0:p1], bandwidth,
+                                                 lambda_, n_chans_divisor, sp)
             return d_err
 
     def _eval_into(self, tile, d_per, d_err, bandwidth, lambda_, n_chans_divisor, sp) -> int:
         """One parrm_eval_periods call on stream ``sp`` (no allocation: capturable); returns
         the number of kernels it enqueued."""
         n_periods = int(d_per.shape[0])
-        check(lib.parrm_eval_periods(
-            _vp(tile.y.data_ptr()), tile.n_chans, _vp(tile.sumsq.data_ptr()),
+        code = tile.y_code
+        check(lib.parrm_eval_periods_typed(
+            _vp(tile.y.data_ptr()), code, tile.n_chans, _vp(tile.sumsq.data_ptr()),
             _vp(tile.indices.data_ptr()), tile.n_chans, tile.n_indices,
             _vp(d_per.data_ptr()), n_periods, int(bandwidth), float(lambda_),
             int(n_chans_divisor), _vp(d_err.data_ptr()),
             _vp(self._eval_ws.data_ptr()), self._eval_ws.numel(), sp), "parrm_eval_periods")
+        if code == _native.F32:  # widened copy (dense float64 [N, C]) + the float64 kernels
+            return 1 + lib.parrm_eval_launch_count(None, tile.n_chans, tile.n_chans,
+                                                   tile.n_indices, n_periods, int(bandwidth))
         return lib.parrm_eval_launch_count(
             _vp(tile.y.data_ptr()), tile.n_chans, tile.n_chans, tile.n_indices, n_periods,
             int(bandwidth))
@@ -420,7 +433,8 @@ class DeviceEngine:
         if bandwidth > _native.MAX_BANDWIDTH:
             raise ValueError(f"bandwidth {bandwidth} exceeds the device limit {_native.MAX_BANDWIDTH}")
         with self._lock, t.cuda.device(self.device):
-            need = lib.parrm_eval_workspace_bytes(tile.n_chans, tile.n_indices, 5 * n, bandwidth)
+            need = lib.parrm_eval_workspace_bytes_typed(tile.n_chans, tile.n_indices, 5 * n,
+                                                        bandwidth, tile.y_code)
             if self._eval_ws is None or self._eval_ws.numel() < need:
                 self._eval_ws = self._empty(need, t.uint8)
             d_starts = t.from_numpy(starts).to(self.device)

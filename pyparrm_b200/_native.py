@@ -55,7 +55,14 @@ SIGNATURES = {
         [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_double,
          c_void_p, c_int64, c_void_p, c_int, c_void_p],
     ),
-    "parrm_channel_sumsq": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "parrm_channel_sumsq": (
+        c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "parrm_eval_workspace_bytes_typed": (c_size_t, [c_int64, c_int64, c_int64, c_int, c_int]),
+    "parrm_eval_periods_typed": (
+        c_int,
+        [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int,
+         c_double, c_int64, c_void_p, c_void_p, c_size_t, c_void_p],
+    ),
     "parrm_standardise_full": (
         c_int,
         [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_double, c_void_p, c_int64, c_int,

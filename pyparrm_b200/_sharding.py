@@ -265,7 +265,8 @@ def minloc_sharded(evaluate, periods: np.ndarray) -> tuple[int, float]:
     return int(best[1]), float(best[0])
 
 
-def prepare_tiles_sharded(engine, data: np.ndarray, index_sets, outlier_boundary: float):
+def prepare_tiles_sharded(engine, data: np.ndarray, index_sets, outlier_boundary: float,
+                          precision: str = "fp64"):
     """Standardised search tiles with the recording read once across ALL ranks: every rank
     standardises its channel block (its rows are the only ones that cross PCIe) and one
     all-gather per tile replicates the ``[samples, channels]`` tiles (<= 51 MB) over NVLink
@@ -274,10 +275,10 @@ def prepare_tiles_sharded(engine, data: np.ndarray, index_sets, outlier_boundary
     world, rank = _world_rank()
     n_chans = data.shape[0]
     if world == 1 or n_chans < world:
-        return engine.prepare_tiles(data, index_sets, outlier_boundary)
+        return engine.prepare_tiles(data, index_sets, outlier_boundary, precision)
     per = -(-n_chans // world)
     c0, c1 = block(n_chans, world, rank)
-    local = engine.prepare_tiles(data[c0:c1], index_sets, outlier_boundary)
+    local = engine.prepare_tiles(data[c0:c1], index_sets, outlier_boundary, precision)
     return [engine.merge_channel_tiles(tile, _all_gather, n_chans, per) for tile in local]
 
 

@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "parrm_b200.h"
 
 namespace parrm {
@@ -37,6 +39,15 @@ inline int cuda_fail(cudaError_t err, const char* what) {
     cudaError_t err__ = cudaGetLastError();                          \
     if (err__ != cudaSuccess) return ::parrm::cuda_fail(err__, name); \
   } while (0)
+
+// NVTX range around a C-ABI call (header-only NVTX 3: a no-op unless a profiler is attached).
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define PARRM_NVTX(name) ::parrm::NvtxRange parrm_nvtx_range__(name)
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 

@@ -279,6 +279,7 @@ int parrm_filter_apply_ex(const void* d_x, int64_t ld_x, int64_t x_t0, int64_t n
                           int64_t ld_out, int64_t t0, int64_t n_out, int64_t n_samples_total,
                           int64_t n_chans, const void* d_plan, const void* h_plan, int dtype,
                           const parrm_filter_options_t* options, void* stream) {
+  PARRM_NVTX("parrm_filter_apply_ex");
   using namespace parrm;
   PARRM_REQUIRE(d_plan != nullptr && h_plan != nullptr, "parrm_filter_apply: null plan");
   const FilterPlanHeader* hdr = static_cast<const FilterPlanHeader*>(h_plan);
@@ -362,6 +363,7 @@ int parrm_filter_apply_batch(const void* d_x, int64_t ld_x, int64_t n_samples, i
                              const int32_t* d_taps, int64_t tap_stride, const int32_t* d_n_taps,
                              int64_t n_sets, int64_t max_half_width, void* d_out, int64_t ld_out,
                              int64_t set_stride, int dtype, void* stream) {
+  PARRM_NVTX("parrm_filter_apply_batch");
   using namespace parrm;
   PARRM_REQUIRE(dtype == PARRM_F64 || dtype == PARRM_F32, "parrm_filter_apply_batch: bad dtype %d", dtype);
   PARRM_REQUIRE(n_sets >= 0 && n_sets <= 65535 && n_chans >= 0 && n_chans <= 65535 && n_samples >= 0,

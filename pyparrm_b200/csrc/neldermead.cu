@@ -185,6 +185,7 @@ int parrm_nm_init(const double* d_starts, int32_t n_chains, void* d_state, doubl
 int parrm_nm_step(void* d_state, int32_t n_chains, const double* d_values, double* d_points,
                   double xtol, double ftol, int32_t maxiter, int32_t maxfun, int32_t* d_n_active,
                   void* stream) {
+  PARRM_NVTX("parrm_nm_step");
   PARRM_REQUIRE(n_chains >= 1 && n_chains <= 1024, "parrm_nm_step: 1..1024 chains");
   PARRM_REQUIRE(d_state && d_values && d_points && d_n_active, "parrm_nm_step: null pointer");
   parrm::nm_step_kernel<<<1, 1024, 0, parrm::as_stream(stream)>>>(

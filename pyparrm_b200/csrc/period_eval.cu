@@ -946,6 +946,16 @@ eval_retile_kernel(const double* __restrict__ y, int64_t ld_y, int64_t n_indices
   }
 }
 
+// float32 storage of the search tile: widened once per call into a dense float64 [N, C] array
+// in the workspace, which the float64 kernels then read (the arithmetic stays float64).
+__global__ void __launch_bounds__(256)
+eval_widen_kernel(const float* __restrict__ y, int64_t ld_y, int64_t n_indices, int64_t n_chans,
+                  double* __restrict__ out) {
+  const int64_t total = n_indices * n_chans;
+  for (int64_t e = int64_t(blockIdx.x) * 256 + threadIdx.x; e < total; e += int64_t(gridDim.x) * 256)
+    out[e] = double(y[(e / n_chans) * ld_y + (e % n_chans)]);
+}
+
 // first index of the smallest non-NaN value
 __global__ void __launch_bounds__(1024)
 argmin_kernel(const double* __restrict__ v, int64_t n, double* min_value, int64_t* min_index) {
@@ -1069,6 +1079,7 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
                        const double* d_periods, int64_t n_periods, int bandwidth, double lambda,
                        int64_t n_chans_divisor, double* d_fit_error, void* d_workspace,
                        size_t workspace_bytes, void* stream) {
+  PARRM_NVTX("parrm_eval_periods");
   using namespace parrm;
   PARRM_REQUIRE(n_chans > 0 && n_indices > 0 && n_periods >= 0 && ld_y >= n_chans,
                 "parrm_eval_periods: bad shape");
@@ -1148,6 +1159,56 @@ int parrm_eval_periods(const double* d_y, int64_t ld_y, const double* d_sumsq,
       ws, d_sumsq, lambda, n_chans_divisor, d_fit_error, sh);
   PARRM_LAUNCH_OK("eval_solve_kernel");
   return PARRM_OK;
+}
+
+// ---- float32 storage of the tile (the "fp32" mode of the search) ---------------------------
+static size_t eval_base_bytes(int64_t n_chans, int64_t n_indices, int64_t n_periods, int bandwidth) {
+  return (parrm_eval_workspace_bytes(n_chans, n_indices, n_periods, bandwidth) + 15) & ~size_t(15);
+}
+
+size_t parrm_eval_workspace_bytes_typed(int64_t n_chans, int64_t n_indices, int64_t n_periods,
+                                        int bandwidth, int y_dtype) {
+  const size_t base = parrm_eval_workspace_bytes(n_chans, n_indices, n_periods, bandwidth);
+  if (y_dtype != PARRM_F32 || base == 0) return base;
+  return eval_base_bytes(n_chans, n_indices, n_periods, bandwidth) +
+         size_t(n_chans) * size_t(n_indices) * sizeof(double);
+}
+
+int parrm_eval_periods_typed(const void* d_y, int y_dtype, int64_t ld_y, const double* d_sumsq,
+                             const int64_t* d_indices, int64_t n_chans, int64_t n_indices,
+                             const double* d_periods, int64_t n_periods, int bandwidth,
+                             double lambda, int64_t n_chans_divisor, double* d_fit_error,
+                             void* d_workspace, size_t workspace_bytes, void* stream) {
+  PARRM_NVTX("parrm_eval_periods_typed");
+  using namespace parrm;
+  if (y_dtype == PARRM_F64)
+    return parrm_eval_periods(static_cast<const double*>(d_y), ld_y, d_sumsq, d_indices, n_chans,
+                              n_indices, d_periods, n_periods, bandwidth, lambda, n_chans_divisor,
+                              d_fit_error, d_workspace, workspace_bytes, stream);
+  PARRM_REQUIRE(y_dtype == PARRM_F32, "parrm_eval_periods_typed: y must be float64 or float32");
+  PARRM_REQUIRE(n_chans > 0 && n_indices > 0 && n_periods >= 0 && ld_y >= n_chans,
+                "parrm_eval_periods_typed: bad shape");
+  if (n_periods == 0) return PARRM_OK;
+  if (bandwidth < 0 || bandwidth > PARRM_MAX_BANDWIDTH) {
+    set_error("parrm_eval_periods: bandwidth %d outside [0, %d]", bandwidth, PARRM_MAX_BANDWIDTH);
+    return PARRM_ERR_UNSUPPORTED;
+  }
+  PARRM_REQUIRE(d_y && d_workspace, "parrm_eval_periods_typed: null pointer");
+  if (workspace_bytes <
+      parrm_eval_workspace_bytes_typed(n_chans, n_indices, n_periods, bandwidth, y_dtype)) {
+    set_error("parrm_eval_periods_typed: workspace too small");
+    return PARRM_ERR_WORKSPACE;
+  }
+  const size_t base = eval_base_bytes(n_chans, n_indices, n_periods, bandwidth);
+  double* wide = reinterpret_cast<double*>(static_cast<unsigned char*>(d_workspace) + base);
+  const int64_t total = n_chans * n_indices;
+  eval_widen_kernel<<<unsigned(min64(ceil_div(total, 256), 8 * kNumSMs)), 256, 0,
+                      as_stream(stream)>>>(static_cast<const float*>(d_y), ld_y, n_indices,
+                                           n_chans, wide);
+  PARRM_LAUNCH_OK("eval_widen_kernel");
+  return parrm_eval_periods(wide, n_chans, d_sumsq, d_indices, n_chans, n_indices, d_periods,
+                            n_periods, bandwidth, lambda, n_chans_divisor, d_fit_error,
+                            d_workspace, base, stream);
 }
 
 int parrm_argmin(const double* d_values, int64_t n, double* d_min_value, int64_t* d_min_index,

@@ -61,6 +61,7 @@ periodogram_kernel(const T* __restrict__ x, int64_t ld, int64_t n_samples, int n
 extern "C" int parrm_periodogram(const void* d_x, int64_t n_chans, int64_t n_samples, int64_t ld,
                                  int dtype, int64_t n_points, double sampling_freq, float* d_psd,
                                  int64_t ld_psd, void* stream) {
+  PARRM_NVTX("parrm_periodogram");
   using namespace parrm;
   PARRM_REQUIRE(n_points >= 2 && n_points <= 16384,
                 "parrm_periodogram: n_points must lie in [2, 16384] (got %lld)", (long long)n_points);

@@ -10,18 +10,60 @@ namespace parrm {
 constexpr int kScaleThreads = 256;
 constexpr int kScaleChunk = 16384;  // diffs per CTA
 
+// 16-byte loads: a thread takes VEC consecutive samples per pass (2 doubles / 4 floats) and the
+// first sample of its right-hand neighbour by shuffle; four passes are in flight per thread.
+// Rows whose base is not 16-byte aligned (odd row stride) take the scalar loop.
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<double> {
+  typedef double2 type;
+  static constexpr int N = 2;
+};
+template <>
+struct Vec16<float> {
+  typedef float4 type;
+  static constexpr int N = 4;
+};
+
 template <typename T>
 __global__ void __launch_bounds__(kScaleThreads)
 abs_diff_partial_kernel(const T* __restrict__ x, int64_t n_diffs, int64_t ld, int n_chunks,
                         double* __restrict__ partial) {
   __shared__ double warp_part[kScaleThreads / 32];
+  typedef typename Vec16<T>::type V;
+  constexpr int N = Vec16<T>::N;
   const int64_t chan = blockIdx.y;
   const T* row = x + chan * ld;
   const int64_t begin = int64_t(blockIdx.x) * kScaleChunk;
   const int64_t end = min(begin + kScaleChunk, n_diffs);
+  const int lane = threadIdx.x & 31;
   double acc = 0.0;
-  for (int64_t t = begin + threadIdx.x; t < end; t += kScaleThreads)
-    acc += fabs(double(row[t + 1] - row[t]));  // difference in the data's own precision
+  int64_t t = begin;
+  if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+    // whole warps of vector passes while every lane's N samples and its neighbour's first
+    // sample exist: lane l covers samples [t0 + l N, t0 + (l + 1) N], diffs t0 + l N .. + N - 1
+    constexpr int kPass = kScaleThreads * N;
+    for (; t + kPass <= end; t += kPass) {
+      const int64_t t0 = t + int64_t(threadIdx.x) * N;
+      const V v = *reinterpret_cast<const V*>(row + t0);
+      T e[N + 1];
+      if (N == 2) {
+        e[0] = reinterpret_cast<const T*>(&v)[0];
+        e[1] = reinterpret_cast<const T*>(&v)[1];
+      } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) e[i] = reinterpret_cast<const T*>(&v)[i];
+      }
+      T next = __shfl_down_sync(0xffffffffu, e[0], 1);
+      if (lane == 31) next = row[t0 + N];  // t0 + N <= end <= n_diffs: a valid sample
+      e[N] = next;
+#pragma unroll
+      for (int i = 0; i < N; ++i) acc += fabs(double(e[i + 1] - e[i]));  // data's own precision
+    }
+  }
+  for (int64_t u = t + threadIdx.x; u < end; u += kScaleThreads)
+    acc += fabs(double(row[u + 1] - row[u]));
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -63,13 +105,17 @@ standardise_gather_kernel(const T* __restrict__ x, int64_t ld, const int64_t* __
   y[j * ld_y + chan] = clip_keep_nan(double(T(d / T(scale[chan]))), bound);  // sample-major
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-channel_sumsq_kernel(const double* __restrict__ y, int64_t ld_y, int64_t n,
+channel_sumsq_kernel(const T* __restrict__ y, int64_t ld_y, int64_t n,
                      double* __restrict__ sumsq) {
   __shared__ double warp_part[8];
-  const double* col = y + blockIdx.x;  // channel blockIdx.x of the sample-major tile
+  const T* col = y + blockIdx.x;  // channel blockIdx.x of the sample-major tile
   double acc = 0.0;
-  for (int64_t j = threadIdx.x; j < n; j += 256) acc = fma(col[j * ld_y], col[j * ld_y], acc);
+  for (int64_t j = threadIdx.x; j < n; j += 256) {
+    const double v = double(col[j * ld_y]);
+    acc = fma(v, v, acc);
+  }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -112,6 +158,7 @@ size_t parrm_channel_scales_workspace_bytes(int64_t n_chans, int64_t n_samples) 
 int parrm_channel_scales(const void* d_x, int64_t n_chans, int64_t n_samples, int64_t ld,
                          double* d_scale, void* d_workspace, size_t workspace_bytes, int dtype,
                          void* stream) {
+  PARRM_NVTX("parrm_channel_scales");
   using namespace parrm;
   PARRM_REQUIRE(n_chans > 0 && n_chans <= 65535 && n_samples >= 1 && ld >= n_samples,
                 "parrm_channel_scales: bad shape (%lld x %lld, ld %lld)", (long long)n_chans,
@@ -147,6 +194,7 @@ int parrm_standardise_gather(const void* d_x, int64_t n_chans, int64_t n_samples
                              const int64_t* d_indices, int64_t n_indices, const double* d_scale,
                              double outlier_boundary, double* d_y, int64_t ld_y, double* d_sumsq,
                              int dtype, void* stream) {
+  PARRM_NVTX("parrm_standardise_gather");
   using namespace parrm;
   PARRM_REQUIRE(n_chans > 0 && n_chans <= 65535 && n_samples >= 2 && ld >= n_samples,
                 "parrm_standardise_gather: bad shape");
@@ -168,7 +216,7 @@ int parrm_standardise_gather(const void* d_x, int64_t n_chans, int64_t n_samples
   }
   PARRM_LAUNCH_OK("standardise_gather_kernel");
   if (d_sumsq) {
-    channel_sumsq_kernel<<<(unsigned)n_chans, 256, 0, s>>>(d_y, ld_y, n_indices, d_sumsq);
+    channel_sumsq_kernel<double><<<(unsigned)n_chans, 256, 0, s>>>(d_y, ld_y, n_indices, d_sumsq);
     PARRM_LAUNCH_OK("channel_sumsq_kernel");
   }
   return PARRM_OK;
@@ -177,6 +225,7 @@ int parrm_standardise_gather(const void* d_x, int64_t n_chans, int64_t n_samples
 int parrm_standardise_full(const void* d_x, int64_t n_chans, int64_t n_samples, int64_t ld,
                            const double* d_scale, double outlier_boundary, void* d_z,
                            int64_t ld_z, int dtype, void* stream) {
+  PARRM_NVTX("parrm_standardise_full");
   using namespace parrm;
   PARRM_REQUIRE(n_chans > 0 && n_chans <= 65535 && n_samples >= 2 && ld >= n_samples &&
                     ld_z >= n_samples - 1,
@@ -204,15 +253,21 @@ int parrm_standardise_full(const void* d_x, int64_t n_chans, int64_t n_samples, 
 }  // extern "C"
 
 // sum_j y[j, c]^2 of a sample-major tile (the y'y term of the evaluator's quadratic form) for
-// callers that bring an already standardised tile (PARRM._optimise_local's seam).
-extern "C" int parrm_channel_sumsq(const double* d_y, int64_t ld_y, int64_t n_chans,
+// callers that bring an already standardised tile (PARRM._optimise_local's seam) and for the
+// float32 storage mode, where the sums must be those of the rounded values the fit sees.
+extern "C" int parrm_channel_sumsq(const void* d_y, int y_dtype, int64_t ld_y, int64_t n_chans,
                                    int64_t n_indices, double* d_sumsq, void* stream) {
   PARRM_REQUIRE(n_chans >= 0 && n_chans <= 65535 && n_indices >= 0 && ld_y >= n_chans,
                 "parrm_channel_sumsq: bad shape");
+  PARRM_REQUIRE(y_dtype == PARRM_F64 || y_dtype == PARRM_F32, "parrm_channel_sumsq: bad dtype");
   if (n_chans == 0) return PARRM_OK;
   PARRM_REQUIRE(d_y != nullptr && d_sumsq != nullptr, "parrm_channel_sumsq: null pointer");
-  parrm::channel_sumsq_kernel<<<unsigned(n_chans), 256, 0, parrm::as_stream(stream)>>>(
-      d_y, ld_y, n_indices, d_sumsq);
+  if (y_dtype == PARRM_F64)
+    parrm::channel_sumsq_kernel<double><<<unsigned(n_chans), 256, 0, parrm::as_stream(stream)>>>(
+        static_cast<const double*>(d_y), ld_y, n_indices, d_sumsq);
+  else
+    parrm::channel_sumsq_kernel<float><<<unsigned(n_chans), 256, 0, parrm::as_stream(stream)>>>(
+        static_cast<const float*>(d_y), ld_y, n_indices, d_sumsq);
   PARRM_LAUNCH_OK("channel_sumsq_kernel");
   return PARRM_OK;
 }

@@ -124,6 +124,7 @@ default_half_width_kernel(const double* __restrict__ period, const double* __res
 extern "C" int parrm_build_taps(double period, double period_half_width,
                                 int64_t filter_half_width, int64_t omit_n_samples, int direction,
                                 int32_t* d_taps, int32_t* d_n_taps, void* stream) {
+  PARRM_NVTX("parrm_build_taps");
   PARRM_REQUIRE(period > 0.0, "parrm_build_taps: period must be > 0");
   PARRM_REQUIRE(filter_half_width >= 0 && filter_half_width < (int64_t(1) << 30),
                 "parrm_build_taps: filter_half_width out of range");
@@ -141,6 +142,7 @@ extern "C" int parrm_build_taps_batch(const double* d_period, const double* d_pe
                                       const int64_t* d_omit_n_samples, const int32_t* d_direction,
                                       int64_t n_sets, int32_t* d_taps, int64_t stride,
                                       int32_t* d_n_taps, void* stream) {
+  PARRM_NVTX("parrm_build_taps_batch");
   PARRM_REQUIRE(n_sets >= 0 && n_sets <= 65535, "parrm_build_taps_batch: 0..65535 parameter sets");
   if (n_sets == 0) return PARRM_OK;
   PARRM_REQUIRE(d_period && d_period_half_width && d_filter_half_width && d_omit_n_samples &&
@@ -157,6 +159,7 @@ extern "C" int parrm_build_taps_batch(const double* d_period, const double* d_pe
 extern "C" int parrm_default_half_width(const double* d_period, const double* d_period_half_width,
                                         const int64_t* d_omit_n_samples, const int64_t* d_limit,
                                         int64_t n_sets, int64_t* d_half_width, void* stream) {
+  PARRM_NVTX("parrm_default_half_width");
   PARRM_REQUIRE(n_sets >= 0 && n_sets <= 65535, "parrm_default_half_width: 0..65535 parameter sets");
   if (n_sets == 0) return PARRM_OK;
   PARRM_REQUIRE(d_period && d_period_half_width && d_omit_n_samples && d_limit && d_half_width,

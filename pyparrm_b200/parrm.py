@@ -67,7 +67,8 @@ class PARRM:
     sampling_freq, artefact_freq : int | float, in Hz
     verbose : bool (default True)
     precision : ``"fp64"`` (default, reference arithmetic) or ``"fp32"`` -- additive,
-        keyword-only; ``"fp32"`` runs the filter kernel in single precision (rel. err <= 1e-4).
+        keyword-only; ``"fp32"`` runs the filter kernel in single precision and keeps the
+        search tiles in float32 (fit in float64); period and output within 1e-4 relative.
     """
 
     _data = None
@@ -260,9 +261,10 @@ class PARRM:
         ]
         if _sharding.active():  # every rank standardises its channel block; tiles all-gathered
             tiles = _sharding.prepare_tiles_sharded(
-                engine, self._data, index_sets, self._outlier_boundary)
+                engine, self._data, index_sets, self._outlier_boundary, self._precision)
         else:
-            tiles = engine.prepare_tiles(self._data, index_sets, self._outlier_boundary)
+            tiles = engine.prepare_tiles(self._data, index_sets, self._outlier_boundary,
+                                         self._precision)
 
         estimated_period = self._assumed_periods
         for run_idx, ((_, _, bandwidth), indices, tile) in enumerate(

@@ -26,7 +26,7 @@ class OracleEngine:
         self.evaluations = 0
         self.rounds = 0
 
-    def prepare_tiles(self, data, index_sets, outlier_boundary):
+    def prepare_tiles(self, data, index_sets, outlier_boundary, precision="fp64"):
         z = oracle.standardise(data, outlier_boundary)
         return [OracleTile(z, np.asarray(idx), len(idx), z.shape[0]) for idx in index_sets]
 

@@ -270,3 +270,40 @@ def test_device_nelder_mead_retraces_host_state_machines(gpu_engine):
         for g, w in zip(got, want):
             assert g[0] == w[0] and (g[1] == w[1] or (np.isnan(g[1]) and np.isnan(w[1])))
             assert g[2:] == (w[2], w[3]), (g, w)
+
+
+@pytest.mark.parametrize("name", ["example_dbs", "synthetic_2x30000", "ecog_lfp"])
+def test_fp32_mode_period_within_1e_4(golden, gpu_engine, name):
+    """BASELINE north_star: the fp32 mode reproduces the reference period to <= 1e-4 relative.
+    Search tiles are stored in float32 (parrm_eval_periods_typed); the fit runs in float64."""
+    import torch
+
+    g = golden(name)
+    if name == "example_dbs":
+        parrm = PARRM(np.load(get_example_data_paths("example_data")), 200, 150, verbose=False,
+                      precision="fp32")
+        parrm.find_period()
+    elif name == "ecog_lfp":
+        parrm = PARRM(np.load(get_example_data_paths("ecog_lfp_data")), 1000, 130, verbose=False,
+                      precision="fp32")
+        parrm.find_period(random_seed=0)
+    else:
+        n_chans, n, fs, fa, seed = (int(v) for v in g["recording"])
+        parrm = PARRM(make_recording(n_chans, n, fs, fa, seed=seed), fs, fa, verbose=False,
+                      precision="fp32")
+        parrm.find_period(random_seed=0)
+    want = float(g["period"])
+    rel = abs(parrm.period - want) / want
+    print(f"{name}: fp32-mode period {parrm.period!r} reference {want!r} rel {rel:.2e}")
+    assert rel <= 1e-4
+    # the evaluator itself: float32 tile vs float64 tile on one grid
+    data = make_recording(5, 30_000, 2000, 130, seed=3)
+    idx = np.arange(2_000, 12_001)
+    t64, = gpu_engine.prepare_tiles(data, [idx], 3.0)
+    t32, = gpu_engine.prepare_tiles(data, [idx], 3.0, precision="fp32")
+    assert t32.y.dtype == torch.float32 and t64.y.dtype == torch.float64
+    periods = (2000 / 130) * (1 + np.linspace(-1e-3, 1e-3, 41))
+    e64 = gpu_engine.evaluate(t64, periods, 10, 1.0, 5)
+    e32 = gpu_engine.evaluate(t32, periods, 10, 1.0, 5)
+    assert np.abs(e32 - e64).max() <= 1e-4 * np.abs(e64).max()
+    assert int(np.argmin(e32)) == int(np.argmin(e64))
