@@ -287,6 +287,40 @@ def golden_objective(ref):
     print(f"objective: {case} cases")
 
 
+def golden_cfg2_objective(ref):
+    """BASELINE cfg2 at full size (64 channels x 1.2 M samples): the reference's objective on
+    the run-3 shape (random index branch, bandwidth 20) for 16 candidates of the run-3 grid
+    spread over it, on all host threads (a whole find_period would take hours).  Also one
+    channel's filtered output for the cfg2 filter, through the reference's filter_data."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    fs, fa, n_chans, n = 2000, 130, 64, 1_200_000
+    data = make_recording(n_chans, n, fs, fa, seed=0)
+    p = ref.PARRM(data=data, sampling_freq=fs, artefact_freq=fa, verbose=False)
+    p._search_samples = np.arange(n - 1)
+    p._outlier_boundary = 3.0
+    p._standardise_data()
+    z = p._standard_data
+    rng = np.random.default_rng(0)
+    idx = [p._get_centre_indices(use_n, ignore, rng)
+           for use_n, ignore in ((5000, 0.0), (10000, 0.0), (25000, 0.95))][-1]
+    grid = p._get_possible_periods((fs / fa * (1 + 3e-6),), 3)
+    pick = grid[np.linspace(0, len(grid) - 1, 16).astype(int)]
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as pool:
+        vals = np.array(list(pool.map(lambda per: p._optimise_local(per, z, idx, 20, 1.0), pick)))
+    out = dict(indices=idx.astype(np.int64), periods=pick, values=vals,
+               recording=np.array([n_chans, n, fs, fa, 0], dtype=np.int64))
+    q = ref.PARRM(data=data[:2], sampling_freq=fs, artefact_freq=fa, verbose=False)
+    q._period = np.float64(fs / fa * (1 + 3e-6))
+    q.create_filter(filter_half_width=2000, filter_direction="both")
+    y = q.filter_data()
+    out["filtered_ch1_head"] = y[1, :4000].copy()
+    out["filtered_ch1_mid"] = y[1, 600000:602000].copy()
+    out.update(meta())
+    np.savez_compressed(os.path.join(GOLDEN, "cfg2_objective.npz"), **out)
+    print(f"cfg2_objective: {len(pick)} candidates, {len(idx)} indices")
+
+
 def golden_filter_edges(ref):
     out = {}
     rng = np.random.default_rng(11)
@@ -361,7 +395,7 @@ def main():
     jobs = dict(
         data=copy_example_recordings, taps=golden_taps, edges=golden_filter_edges,
         objective=golden_objective, example=golden_example_dbs,
-        synthetic=golden_synthetic, ecog=golden_ecog, psd=golden_psd,
+        synthetic=golden_synthetic, ecog=golden_ecog, psd=golden_psd, cfg2=golden_cfg2_objective,
     )
     for name, job in jobs.items():
         if not only or name in only:

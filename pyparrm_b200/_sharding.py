@@ -112,6 +112,28 @@ def _pci_address(device_index: int) -> str | None:
         return None
 
 
+def _nvml_cpu_affinity(device_index: int) -> list[int]:
+    """CPUs NVML reports as local to the GPU (the "CPU Affinity" column of nvidia-smi topo)."""
+    try:
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device_index)
+        handle = pynvml.nvmlDeviceGetHandleByUUID(f"GPU-{props.uuid}".encode())
+        n_words = (os_cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, n_words)
+        return [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+    except Exception:  # noqa: BLE001 - topology is optional
+        return []
+
+
+def os_cpu_count() -> int:
+    import os
+
+    return os.cpu_count() or 1
+
+
 def bind_host_to_gpu(device_index: int) -> list[int]:
     """Pin this process to the CPUs local to a GPU's PCIe root before it allocates pinned memory.
 
@@ -122,13 +144,17 @@ def bind_host_to_gpu(device_index: int) -> list[int]:
     """
     import os
 
+    cpus: list[int] = []
     address = _pci_address(device_index)
-    if address is None:
-        return []
-    try:
-        with open(f"/sys/bus/pci/devices/{address}/local_cpulist") as f:
-            cpus = _parse_cpulist(f.read())
-    except (OSError, ValueError):
+    if address is not None:
+        try:
+            with open(f"/sys/bus/pci/devices/{address}/local_cpulist") as f:
+                cpus = _parse_cpulist(f.read())
+        except (OSError, ValueError):
+            cpus = []
+    if not cpus:  # containers often hide sysfs topology: ask the driver (NVML) instead
+        cpus = _nvml_cpu_affinity(device_index)
+    if not cpus:
         return []
     allowed = sorted(set(cpus) & os.sched_getaffinity(0))
     if not allowed:
