@@ -669,6 +669,39 @@ def bench_strong(engine, dist, world, rank):
             "roofline_frac": 16.0 * 256 * 3_600_000 * steps / sec3 / 1e9 / hbm_peak,
         }
         del d_x, d_y
+    # ---- cfg3 search shape: 256 channels x 1e5 search samples, dense candidate sweep ------
+    # (what find_period(assumed_periods=<8 values>) evaluates per run: 8 x 388 candidates)
+    from pyparrm_b200 import _native
+    from pyparrm_b200._engine import SearchTile, _vp
+
+    n3, c3 = 100_000, 256
+    y3 = torch.randn((n3, c3), dtype=torch.float64, device="cuda", generator=gen).clamp_(-3.0, 3.0)
+    ss3 = torch.empty(c3, dtype=torch.float64, device="cuda")
+    _native.check(_native.lib.parrm_channel_sumsq(_vp(y3.data_ptr()), _native.F64, c3, c3, n3,
+                                                  _vp(ss3.data_ptr()), _vp(stream.cuda_stream)),
+                  "parrm_channel_sumsq")
+    tile3 = SearchTile(y=y3, sumsq=ss3, indices=torch.arange(n3, dtype=torch.int64, device="cuda"),
+                       n_indices=n3, n_chans=c3)
+    p3 = 1000 / 145
+    grid3 = np.unique(np.concatenate([
+        pk * np.concatenate((1 + np.arange(-1e-2, 1e-2 + 1e-4, 1e-4), 1 + np.arange(-1e-3, 1e-3 + 1e-5, 1e-5)))
+        for pk in p3 * (1 + 0.03 * np.arange(8))]))
+    lo3, hi3 = _sharding.block(len(grid3), world, rank) if world > 1 else (0, len(grid3))
+    mine3 = grid3[lo3:hi3]
+    engine.evaluate_device(tile3, mine3[:64], 20, 1.0, c3)
+    barrier(dist)
+    start.record(stream)
+    engine.evaluate_device(tile3, mine3, 20, 1.0, c3)
+    stop.record(stream)
+    barrier(dist)
+    sec = max_over_ranks(dist, start.elapsed_time(stop) * 1e-3)
+    out["cfg3_search"] = {
+        "workload": f"cfg3 search shape: {len(grid3)} candidates (8 assumed periods x the run-1 grid) x "
+                    f"{n3} contiguous samples x {c3} channels, bandwidth 20; synthetic tile on the "
+                    "device; candidates in contiguous blocks per GPU",
+        "value": len(grid3) / sec, "unit": "candidates/s", "seconds": sec, "scaling": "strong",
+    }
+    del y3, tile3
     # ---- cfg5: candidate sweep, winner only -------------------------------------------
     n_cand, n_fit = 100_000, 100_000
     rng = np.random.default_rng(7)

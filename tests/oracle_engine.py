@@ -69,3 +69,27 @@ class OracleEngine:
         full = np.zeros((chunk.shape[0], n_total))
         full[:, x0:x0 + chunk.shape[1]] = chunk
         return oracle.apply_filter_direct(full, taps)[:, t0:t1]
+
+    # ---- parameter sweeps / spectrum (host logic of PARRM.filter_sweep, compute_psd) -----------
+    def default_half_widths(self, periods, period_half_widths, omits, limit):
+        return np.array([oracle.default_half_width(p, w, int(o), 2 * int(limit) + 1)
+                         for p, w, o in zip(periods, period_half_widths, omits)], dtype=np.int64)
+
+    def filter_sweep(self, data, periods, period_half_widths, half_widths, omits, directions):
+        data = np.asarray(data, dtype=np.float64)
+        out = np.zeros((len(half_widths),) + data.shape)
+        taps_all = []
+        for k, (p, w, hw, om, d) in enumerate(zip(periods, period_half_widths, half_widths, omits,
+                                                  directions)):
+            taps = oracle.tap_offsets(p, w, int(hw), int(om), d)
+            taps_all.append(taps)
+            if len(taps):
+                out[k] = oracle.apply_filter_direct(data, taps)
+        return out, taps_all
+
+    def periodogram(self, data, n_points, sampling_freq):
+        x = np.asarray(data).astype(np.float32)
+        coeffs = np.fft.fft(x, int(n_points))[..., 1:(int(n_points) // 2) + 1]
+        return ((1.0 / (sampling_freq * n_points)) * np.abs(coeffs).astype(np.float32) ** 2).astype(
+            np.float32)
+

@@ -252,3 +252,55 @@ def test_example_data_registry():
         assert np.load(get_example_data_paths(name)).ndim == 2
     with pytest.raises(ValueError, match="`name` must be one of"):
         get_example_data_paths("nope")
+
+
+def test_filter_sweep_host_logic(cpu_engine):
+    """PARRM.filter_sweep: defaults, validation with create_filter's messages, per-set results
+    equal to create_filter + filter_data one by one (stand-in engine; the GPU test covers the
+    batched kernels)."""
+    from pyparrm_b200 import PARRM
+    from pyparrm_b200.synthetic import make_recording
+
+    data = make_recording(2, 5000, 200, 13, seed=1)
+    parrm = PARRM(data, 200, 13, verbose=False)
+    with pytest.raises(ValueError, match="The period has not yet been estimated"):
+        parrm.filter_sweep([{}])
+    parrm._period = np.float64(200 / 13)
+    sets = [dict(), dict(filter_half_width=500, filter_direction="past"),
+            dict(omit_n_samples=3, period_half_width=0.5)]
+    out, taps = parrm.filter_sweep(sets)
+    assert out.shape == (3, 2, 5000) and parrm._filter is None   # object's own filter untouched
+    for k, s in enumerate(sets):
+        single = PARRM(data, 200, 13, verbose=False)
+        single._period = parrm._period
+        single.create_filter(**s)
+        assert np.array_equal(taps[k], np.flatnonzero(single.filter < 0) - single._filter_half_width)
+        assert np.array_equal(out[k], single.filter_data())
+    for bad, exc, msg in (
+        (dict(omit_n_samples=1.5), TypeError, "`omit_n_samples` must be an int."),
+        (dict(omit_n_samples=-1), ValueError, "`omit_n_samples` must lie in the range"),
+        (dict(period_half_width="a"), TypeError, "`period_half_width` must be an int or a float."),
+        (dict(period_half_width=100.0), ValueError, "`period_half_width` must be lie in the range"),
+        (dict(filter_half_width=2.0), TypeError, "`filter_half_width` must be an int."),
+        (dict(filter_half_width=2, omit_n_samples=5), ValueError, "`filter_half_width` must lie in"),
+        (dict(filter_direction=1), TypeError, "`filter_direction` must be a str."),
+        (dict(filter_direction="up"), ValueError, "`filter_direction` must be one of"),
+    ):
+        with pytest.raises(exc, match=msg):
+            parrm.filter_sweep([bad])
+
+
+def test_compute_psd_wrapper_quirks(cpu_engine):
+    """pyparrm_b200._utils._power.compute_psd: frequency axis, max_freq cut, and the
+    reference's `psd[:-1] *= 2` (all ROWS but the last of a 2-D input, all BINS but the last of
+    a 1-D input), against the oracle's restatement of _utils/_power.py:10-68."""
+    from oracle import parrm_oracle as oracle
+    from pyparrm_b200._utils._power import compute_psd
+
+    rng = np.random.default_rng(44)
+    for shape, fs, n, fmax in (((2, 100), 20, 10, None), ((3, 64), 100, 32, 30.0), ((50,), 20, 16, None)):
+        x = rng.standard_normal(shape)
+        freqs, psd = compute_psd(data=x, sampling_freq=fs, n_points=n, max_freq=fmax, n_jobs=2)
+        f_want, p_want = oracle.periodogram(x, fs, n, fmax)
+        assert np.array_equal(freqs, f_want) and psd.dtype == np.float32
+        assert psd.shape == p_want.shape and np.allclose(psd, p_want, rtol=1e-6, atol=0)
