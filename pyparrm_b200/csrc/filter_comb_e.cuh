@@ -202,19 +202,23 @@ __device__ __forceinline__ T edge_value(const int32_t* __restrict__ count,
 // offset with a box and cancels it with a -1 term (NaN - NaN does not cancel).  It runs after
 // the piece, over the span of steps the step loop flagged, so that the loop itself holds no
 // call (a call in a cold branch still makes the compiler rebuild addresses after the join).
-__device__ __noinline__ T direct_value(const Args& a, const T* __restrict__ xrow, int64_t t,
-                                       int64_t lo_valid, int64_t hi_valid) {
+// (Everything by value: taking the address of the kernel's parameter struct would move it from
+// the constant bank to local memory for the whole kernel.)
+__device__ __noinline__ T direct_value(const int32_t* __restrict__ taps,
+                                       const T2* __restrict__ recip, int64_t n_total, T t_max,
+                                       const T* __restrict__ xrow, int64_t t, int64_t lo_valid,
+                                       int64_t hi_valid) {
   T acc = T(0);
   int n_in = 0;
   for (int k = 0; k < NTAPS; ++k) {
-    const int64_t g = t - a.taps[k];
-    if (g < 0 || g >= a.n_total) continue;
+    const int64_t g = t - taps[k];
+    if (g < 0 || g >= n_total) continue;
     ++n_in;
     if (g >= lo_valid && g < hi_valid) acc += xrow[g];
   }
   if (n_in == 0) return T(0);
-  const T y = xrow[t] - acc * T(a.recip[n_in]);
-  return fabs(y) <= a.t_max ? y : T(0);
+  const T y = xrow[t] - acc * T(recip[n_in]);
+  return fabs(y) <= t_max ? y : T(0);
 }
 
 // A consumer thread's position in the chunk sequence of its piece.
@@ -433,6 +437,8 @@ extern "C" __global__ void __launch_bounds__(NT, PE_CTAS) parrm_filter_comb_e(co
       for (int i = 0; i < n_chunks; ++i) {
         const int64_t g0 = gamma + (c_first + i) * int64_t(CH);
         T* const dst = ring + fslot * CH;
+        // (a nanosleep back-off in this wait was measured: no gain with two CTAs per SM, and
+        // -15 % with one, where a late refill stalls every consumer warp)
         mbar_wait(bars + (Q + fslot) * 8, fphase ^ 1u);  // the previous fill has been released
         if (g0 >= lo_valid && g0 + CH <= hi_valid) {
           if (lane == 0) {
@@ -505,7 +511,7 @@ extern "C" __global__ void __launch_bounds__(NT, PE_CTAS) parrm_filter_comb_e(co
       for (int k = bad_lo; k <= bad_hi; ++k) {
         const int64_t t = T0 + c + int64_t(k) * D;
         if (t >= a.t0 && t < a.t0 + a.n_out)
-          orow[t] = direct_value(a, xrow, t, lo_valid, hi_valid);
+          orow[t] = direct_value(a.taps, a.recip, a.n_total, a.t_max, xrow, t, lo_valid, hi_valid);
       }
     }
     // release the rest of the window (chunks the last group still held)

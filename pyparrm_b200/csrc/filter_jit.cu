@@ -176,19 +176,25 @@ bool comb_e_shape(const FilterPlanHeader* hdr, const int32_t* terms, int dtype,
   s.fwd = -lo;
   if (s.d < kPatternFirstMinStride || s.d > kPatternFirstMaxStride) return false;
   if (n_all > 96 || s.nb[0] < 1) return false;
-  // Occupancy first, then chunk size.  Measured at the cfg2 shape (fraction of the HBM
-  // roofline): two CTAs per SM 64 % with 16 KB chunks, 57 % with 8 KB, 54 % with 6 KB; one CTA
-  // per SM 37-51 %.  Two CTAs per SM need the register rings (live: M0 + M1 values) to leave
-  // ~50 registers for the rest of the step inside the per-thread budget at that occupancy,
-  // and ring + mirror chunks inside half the shared memory.  A chunk is U steps of d samples,
-  // a whole number of 16-byte units; the step loop is unrolled B = U * ceil(M0 / U) deep.
+  // Shape choice, from interleaved A/B runs on one box (scripts/ab_filter_shapes.py, fraction of
+  // the HBM roofline at full size): (1) two CTAs per SM whenever the register rings (live:
+  // M0 + M1 values) leave ~50 registers for the rest of the step inside the per-thread budget
+  // at that occupancy, even at the price of a few spilled bytes -- cfg3 (M0 + M1 = 37): 0.69-0.75
+  // with two CTAs, 0.60 with one; cfg2: 0.70 / 0.68.  (2) a chunk of U steps with U a divisor
+  // of M0, so that the unrolled block B = U * ceil(M0 / U) is exactly M0 steps -- cfg3 U = 5
+  // (B = 25) 0.69-0.75, U = 7 (B = 28) 0.65-0.69; cfg4 U = 10 0.63-0.64, U = 8 (B = 16) 0.58-0.64;
+  // cfg1 U = 5 0.61, U = 3 0.60 -- the largest such chunk up to 32 KB that fits shared memory;
+  // without a usable divisor, the largest chunk up to 20 KB.  A chunk is a whole number of
+  // 16-byte units.
   const int ring_regs = (s.m[0] + (s.nk > 1 ? s.m[1] : 0)) * (s.es / 4);
   const int threads = ((s.d + 31) / 32) * 32 + 32;
   auto reg_budget = [&](int ctas) { return std::min(255, (65536 / (ctas * threads)) / 8 * 8); };
   if (ring_regs + 52 > reg_budget(1)) return false;
-  int ctas_first = ring_regs + 60 <= reg_budget(2) ? 2 : 1;  // 52 spills at the cfg3 shape
+  int ctas_first = ring_regs + 52 <= reg_budget(2) ? 2 : 1;
   if (tune && tune->ctas_per_sm > 0) ctas_first = tune->ctas_per_sm;
-  const int pf_max = (tune && tune->prefetch_chunks > 0) ? tune->prefetch_chunks : 4;
+  // chunks in flight beyond the window: 2 measured best wherever more would fit (cfg3 shape,
+  // one CTA per SM: 0.637 of the HBM roofline with 2, 0.606 with 4; cfg1 taps: 0.591 / 0.582)
+  const int pf_max = (tune && tune->prefetch_chunks > 0) ? tune->prefetch_chunks : 2;
   const int pf_min = std::min(pf_max, 2);
   auto smem_for = [&](int u, int pf) {
     const int64_t ch = int64_t(u) * s.d;
@@ -206,6 +212,10 @@ bool comb_e_shape(const FilterPlanHeader* hdr, const int32_t* terms, int dtype,
       u = tune->steps_per_chunk;
       if (!usable(u) || smem_for(u, pf_min) > budget) u = 0;
     } else {
+      for (int cand = s.m[0]; cand >= 1 && u == 0; --cand)  // largest divisor of M0, <= 32 KB
+        if (s.m[0] % cand == 0 && int64_t(cand) * s.d * s.es <= 32768 &&
+            int64_t(cand) * s.d * s.es >= 4096 && usable(cand) && smem_for(cand, pf_min) <= budget)
+          u = cand;
       const int u_hi = int(std::max<int64_t>(1, 20480 / (int64_t(s.d) * s.es)));
       for (int cand = u_hi; cand >= 1 && u == 0; --cand)  // largest chunk <= 20 KB that fits
         if (usable(cand) && smem_for(cand, pf_min) <= budget) u = cand;

@@ -109,11 +109,11 @@ if __name__ == "__main__":
         return [{}] + [{"steps_per_chunk": u, "prefetch_chunks": pf, "ctas_per_sm": c}
                        for u in us for pf in pfs for c in ctas]
 
-    rows = timing("cfg2", 64, 1_200_000, grid((5, 10), (2,), (2,)))
-    rows += timing("cfg3", 64, 1_200_000, grid((5, 7, 9, 13), (2, 4)))
-    rows += timing("cfg4", 64, 1_200_000, grid((4, 8, 10), (2,)))
-    rows += timing("cfg4f", 64, 1_200_000, grid((8,), (2,), (2,)))
-    rows += timing("cfg1", 64, 1_200_000, grid((1, 2, 3), (2, 4), (1,)))
+    rows = timing("cfg2", 64, 1_200_000, [{}])
+    rows += timing("cfg3", 64, 1_200_000, [{}, {"prefetch_chunks": 3}, {"prefetch_chunks": 4}])
+    rows += timing("cfg4", 64, 1_200_000, [{}, {"steps_per_chunk": 8, "prefetch_chunks": 2, "ctas_per_sm": 1}])
+    rows += timing("cfg4f", 64, 1_200_000, [{}])
+    rows += timing("cfg1", 64, 1_200_000, [{}])
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/check_comb_e.jsonl", "w") as f:
         for r in rows:
