@@ -33,7 +33,9 @@ class FilterOptions(ctypes.Structure):
         ("steps_per_chunk", c_int32),
         ("prefetch_chunks", c_int32),
         ("ctas_per_sm", c_int32),
-        ("reserved", c_int32 * 4),
+        ("variant", c_int32),
+        ("reserved", c_int32),
+        ("timeline", ctypes.c_uint64),
     ]
 
 

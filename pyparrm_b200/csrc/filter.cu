@@ -253,7 +253,8 @@ int parrm_filter_specialise_check(const void* h_plan, int dtype,
   const int32_t* h_terms = reinterpret_cast<const int32_t*>(
       static_cast<const unsigned char*>(h_plan) + hdr->terms_offset);
   FilterTuning tune{0, options ? options->steps_per_chunk : 0,
-                    options ? options->prefetch_chunks : 0, options ? options->ctas_per_sm : 0};
+                    options ? options->prefetch_chunks : 0, options ? options->ctas_per_sm : 0,
+                    options ? options->variant : 0, options ? options->timeline : 0};
   CombEShape s;
   if (!comb_e_shape(hdr, h_terms, dtype, &tune, &s)) {
     set_error("parrm_filter_specialise_check: this plan is outside the specialised kernel's range");
@@ -320,7 +321,8 @@ int parrm_filter_apply_ex(const void* d_x, int64_t ld_x, int64_t x_t0, int64_t n
   if (hdr->kind == kPlanComb &&
       (want == PARRM_FILTER_KERNEL_AUTO || want == PARRM_FILTER_KERNEL_SPECIALISED)) {
     FilterTuning tune{want, options ? options->steps_per_chunk : 0,
-                      options ? options->prefetch_chunks : 0, options ? options->ctas_per_sm : 0};
+                      options ? options->prefetch_chunks : 0, options ? options->ctas_per_sm : 0,
+                    options ? options->variant : 0, options ? options->timeline : 0};
     CombEShape shape;
     const bool fits = comb_e_shape(hdr, h_terms, dtype, &tune, &shape);
     const bool worth = want == PARRM_FILTER_KERNEL_SPECIALISED ||
@@ -331,7 +333,7 @@ int parrm_filter_apply_ex(const void* d_x, int64_t ld_x, int64_t x_t0, int64_t n
           shape, d_x, d_out, d_taps,
           reinterpret_cast<const int32_t*>(d_base + hdr->count_offset),
           reinterpret_cast<const double*>(d_base + hdr->recip_offset), ld_x, x_t0, n_x, ld_out,
-          t0, n_out, n_samples_total, n_chans, s, nullptr);
+          t0, n_out, n_samples_total, n_chans, s, nullptr, tune.timeline);
       if (rc == PARRM_OK) {
         g_last_kernel = "parrm_filter_comb_e";
         return rc;

@@ -64,6 +64,9 @@ typedef unsigned long long uintptr_t;
 #define PE_FWD 2000
 #define PE_CTAS 2
 #endif
+#ifndef PE_VARIANT
+#define PE_VARIANT 0  // bit mask of source variants kept for A/B measurements (filter options)
+#endif
 
 namespace parrm_e {
 
@@ -129,9 +132,12 @@ struct Args {
   int64_t ld_x, x_t0, n_x;
   int64_t ld_out, t0, n_out;
   int64_t n_total;
-  int64_t total_groups;  // n_chans * groups_per_chan
+  int64_t total_groups;  // n_chans * (groups_per_chan + edge_total): the cost units CTAs share
   int32_t groups_per_chan;
+  int32_t edge_start;    // cost of starting a channel (priming, window fill, edge blocks), in groups
+  int32_t edge_total;    // ... of starting and ending it
   int32_t pad;
+  unsigned long long* timeline;  // profiling aid (PE_VARIANT & 2): 4 words per CTA, or null
   T neg_inv_n;  // -1 / NTAPS   (kernel parameters: FP64 instructions take them as constant-bank
   T t_max;      // largest finite T           operands, so they occupy no registers in the loop)
 };
@@ -238,8 +244,8 @@ __device__ __forceinline__ void group_begin(Walk& w, uint32_t bars) {
   }
 }
 // Closes a group: its oldest chunk is released to the producer.
-__device__ __forceinline__ void group_end(Walk& w, uint32_t bars, int lane) {
-  __syncwarp();
+__device__ __forceinline__ void group_end(Walk& w, uint32_t bars, int lane, unsigned wmask) {
+  __syncwarp(wmask);
   if (lane == 0) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + (Q + w.rslot) * 8)
                  : "memory");
@@ -289,7 +295,7 @@ __device__ __forceinline__ T ring_sum1(const Rings& r, int s) {
 template <bool FAST>
 __device__ __forceinline__ int run_block(Rings& r, Walk& w, const Args& a,
                                          const unsigned char* const smem, uint32_t bars,
-                                         int lane, int c, bool lane_stores, T* const orow,
+                                         int lane, unsigned wmask, int c, T* const orow,
                                          int& bad_lo, int& bad_hi, int64_t Tb, int g,
                                          int n_groups) {
   const T neg_inv_n = a.neg_inv_n;
@@ -363,7 +369,7 @@ __device__ __forceinline__ int run_block(Rings& r, Walk& w, const Args& a,
           bad_hi = max(bad_hi, g * U + s);
           y = T(0);
         }
-        if (lane_stores) op[s * D] = y;
+        if (!(PE_VARIANT & 1) || c == threadIdx.x) op[s * D] = y;
       } else if (mode != 0) {
         const int64_t t = Tb + c + int64_t(s) * D;
         T y = mode == 1 ? fma(tot, neg_inv_n, xc) : edge_value(a.count, a.recip, t, a.n_total, xc, tot);
@@ -374,10 +380,10 @@ __device__ __forceinline__ int run_block(Rings& r, Walk& w, const Args& a,
           bad_hi = max(bad_hi, g * U + s);
           y = T(0);
         }
-        if (lane_stores && t >= a.t0 && t < a.t0 + a.n_out) op[s * D] = y;
+        if ((!(PE_VARIANT & 1) || c == threadIdx.x) && t >= a.t0 && t < a.t0 + a.n_out) op[s * D] = y;
       }
     }
-    group_end(w, bars, lane);
+    group_end(w, bars, lane, wmask);
     ++done;
   }
   return done;
@@ -403,7 +409,17 @@ extern "C" __global__ void __launch_bounds__(NT, PE_CTAS) parrm_filter_comb_e(co
 
   const int64_t lo_valid = max64(0, a.x_t0);
   const int64_t hi_valid = min64(a.n_total, a.x_t0 + a.n_x);
+#if PE_VARIANT & 2
+  unsigned long long tl_start = 0, tl_pieces = 0;
+  if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl_start));
+#endif
   const int gpc = a.groups_per_chan;
+  // Strips of equal COST, not equal length: a strip that crosses a channel boundary pays a
+  // second priming block, a second window fill and the slower generic blocks of both recording
+  // edges (measured per CTA, scripts/filter_timeline.py: +18 us on 238 us at the cfg2 shape,
+  // and the kernel ends with its slowest CTA).  Every channel is therefore edge_total cost
+  // units longer than its groups, edge_start of them in front.
+  const int vpc = gpc + a.edge_total;
   const int64_t G_begin = a.total_groups * int64_t(blockIdx.x) / int64_t(gridDim.x);
   const int64_t G_end = a.total_groups * int64_t(blockIdx.x + 1) / int64_t(gridDim.x);
   const uint32_t bars = smem_u32(smem_raw);
@@ -416,10 +432,13 @@ extern "C" __global__ void __launch_bounds__(NT, PE_CTAS) parrm_filter_comb_e(co
   int rslot = 0;        // consumer: oldest live slot (next to release)
 
   for (int64_t G = G_begin; G < G_end;) {
-    const int64_t chan = G / gpc;
-    const int s0 = int(G - chan * gpc);
-    const int s1 = int(min64(gpc, s0 + (G_end - G)));
-    G += s1 - s0;
+    const int64_t chan = G / vpc;
+    const int v0 = int(G - chan * vpc);
+    const int v1 = int(min64(vpc, v0 + (G_end - G)));
+    G += v1 - v0;
+    const int s0 = min(max(v0 - a.edge_start, 0), gpc);
+    const int s1 = min(max(v1 - a.edge_start, 0), gpc);
+    if (s1 <= s0) continue;
     const T* const xrow = a.x + chan * a.ld_x - a.x_t0;  // xrow[g] = sample at global time g
     T* const orow = a.out + chan * a.ld_out - a.t0;      // orow[g]
     const int gamma = int((VEC - int((reinterpret_cast<uintptr_t>(xrow) / ES) % VEC)) % VEC);
@@ -428,6 +447,9 @@ extern "C" __global__ void __launch_bounds__(NT, PE_CTAS) parrm_filter_comb_e(co
     const int64_t n_first = j_first + s0;                      // first group with outputs
     const int64_t n_end = min64(j_first + s1, j_last + 1);
     if (n_first >= n_end) continue;
+#if PE_VARIANT & 2
+    ++tl_pieces;
+#endif
     const int n_groups = NPG + int(n_end - n_first);           // priming groups first
     const int n_chunks = n_groups + HB + HF;
     const int64_t c_first = n_first - NPG - HB;                // first chunk the piece reads
@@ -467,8 +489,16 @@ extern "C" __global__ void __launch_bounds__(NT, PE_CTAS) parrm_filter_comb_e(co
     }
 
     // ------------------------------ consumer warps ------------------------------
-    const int c = tid < D ? tid : D - 1;  // lanes past the last chain shadow it (no stores)
-    const bool lane_stores = tid < D;
+    // Lanes past the last chain idle: a half-warp with no active lane costs the shared-memory
+    // pipe no wavefront (D = 200: 1 of 14 wavefronts per load instruction of the CTA).
+#if PE_VARIANT & 1  // A/B: the lanes past the last chain shadow it instead
+    const int c = tid < D ? tid : D - 1;
+    const unsigned wmask = 0xffffffffu;
+#else
+    if (tid >= D) continue;
+    const int c = tid;
+    const unsigned wmask = (tid | 31) < D ? 0xffffffffu : ((1u << (D & 31)) - 1u);
+#endif
     for (int i = 0; i < HB + HF; ++i) {   // the window of the first group, except its newest chunk
       mbar_wait(bars + fslot * 8, fphase);
       if (++fslot == Q) {
@@ -497,30 +527,41 @@ extern "C" __global__ void __launch_bounds__(NT, PE_CTAS) parrm_filter_comb_e(co
                         Tb + int64_t(B) * D - WLO <= a.n_total && Tb >= a.t0 &&
                         Tb + int64_t(B) * D <= a.t0 + a.n_out;
       if (fast) {
-        g += run_block<true>(r, w, a, smem_raw, bars, lane, c, lane_stores, orow, bad_lo, bad_hi,
+        g += run_block<true>(r, w, a, smem_raw, bars, lane, wmask, c, orow, bad_lo, bad_hi,
                              Tb, g, n_groups);
       } else {
-        g += run_block<false>(r, w, a, smem_raw, bars, lane, c, lane_stores, orow, bad_lo,
-                              bad_hi, Tb, g, n_groups);
+        g += run_block<false>(r, w, a, smem_raw, bars, lane, wmask, c, orow, bad_lo, bad_hi,
+                              Tb, g, n_groups);
       }
     }
     rslot = w.rslot;
     fslot = w.fslot;
     fphase = w.fphase;
-    if (lane_stores) {  // rare: re-evaluate the flagged span by the definition
-      for (int k = bad_lo; k <= bad_hi; ++k) {
-        const int64_t t = T0 + c + int64_t(k) * D;
-        if (t >= a.t0 && t < a.t0 + a.n_out)
-          orow[t] = direct_value(a.taps, a.recip, a.n_total, a.t_max, xrow, t, lo_valid, hi_valid);
-      }
+    for (int k = bad_lo; k <= bad_hi; ++k) {  // rare: re-evaluate the flagged span by the definition
+      if ((PE_VARIANT & 1) && c != tid) break;
+      const int64_t t = T0 + c + int64_t(k) * D;
+      if (t >= a.t0 && t < a.t0 + a.n_out)
+        orow[t] = direct_value(a.taps, a.recip, a.n_total, a.t_max, xrow, t, lo_valid, hi_valid);
     }
     // release the rest of the window (chunks the last group still held)
-    __syncwarp();
+    __syncwarp(wmask);
     for (int i = 0; i < HB + HF; ++i) {
       if (lane == 0) mbar_arrive(&empty[rslot]);
       if (++rslot == Q) rslot = 0;
     }
   }
+#if PE_VARIANT & 2
+  if (tid == 0 && a.timeline) {
+    unsigned long long tl_end;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl_end));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    a.timeline[4 * blockIdx.x + 0] = smid;
+    a.timeline[4 * blockIdx.x + 1] = tl_start;
+    a.timeline[4 * blockIdx.x + 2] = tl_end;
+    a.timeline[4 * blockIdx.x + 3] = tl_pieces;
+  }
+#endif
 }
 
 }  // namespace parrm_e

@@ -229,6 +229,7 @@ bool comb_e_shape(const FilterPlanHeader* hdr, const int32_t* terms, int dtype,
     s.ctas = ctas;
     s.u = u;
     s.pf = pf;
+    s.variant = tune ? tune->variant : 0;
     *out = s;
     return true;
   }
@@ -255,7 +256,7 @@ static int compile_cubin(const CombEShape& s, std::vector<char>* cubin) {
       "-DPE_PF=" + std::to_string(s.pf), "-DPE_NTAPS=" + std::to_string(s.n_taps),
       "-DPE_WLO=" + std::to_string(s.w_lo), "-DPE_WHI=" + std::to_string(s.w_hi),
       "-DPE_BACK=" + std::to_string(s.back), "-DPE_FWD=" + std::to_string(s.fwd),
-      "-DPE_CTAS=" + std::to_string(s.ctas)};
+      "-DPE_CTAS=" + std::to_string(s.ctas), "-DPE_VARIANT=" + std::to_string(s.variant)};
   std::vector<const char*> copts;
   for (const std::string& o : opts) copts.push_back(o.c_str());
   nvrtcProgram prog = nullptr;
@@ -338,7 +339,8 @@ std::string comb_e_key(const CombEShape& s, int dev) {
                     join(s.minus, s.n_minus) + "|" + std::to_string(s.centre) + "|" +
                     std::to_string(s.u) + "|" + std::to_string(s.pf) + "|" +
                     std::to_string(s.n_taps) + "|" + std::to_string(s.w_lo) + "|" +
-                    std::to_string(s.w_hi) + "|" + std::to_string(s.ctas);
+                    std::to_string(s.w_hi) + "|" + std::to_string(s.ctas) + "|" +
+                    std::to_string(s.variant);
   return key;
 }
 
@@ -348,7 +350,7 @@ int launch_comb_e(const CombEShape& s, const void* d_x, void* d_out, const int32
                   const int32_t* d_count, const double* d_recip,
                   int64_t ld_x, int64_t x_t0, int64_t n_x, int64_t ld_out, int64_t t0,
                   int64_t n_out, int64_t n_total, int64_t n_chans, cudaStream_t stream,
-                  int* regs_out) {
+                  int* regs_out, unsigned long long timeline) {
   int dev = 0;
   PARRM_CUDA_OK(cudaGetDevice(&dev));
   const std::string key = comb_e_key(s, dev);
@@ -372,7 +374,8 @@ int launch_comb_e(const CombEShape& s, const void* d_x, void* d_out, const int32
     const int32_t* count;
     const double* recip;
     int64_t ld_x, x_t0, n_x, ld_out, t0, n_out, n_total, total_groups;
-    int32_t groups_per_chan, pad;
+    int32_t groups_per_chan, edge_start, edge_total, pad;
+    unsigned long long timeline;
     unsigned char consts[16];  // T neg_inv_n, t_max in the kernel's element type
   } a;
   a.x = d_x; a.out = d_out; a.taps = d_taps; a.count = d_count; a.recip = d_recip;
@@ -380,8 +383,17 @@ int launch_comb_e(const CombEShape& s, const void* d_x, void* d_out, const int32
   a.ld_out = ld_out; a.t0 = t0; a.n_out = n_out; a.n_total = n_total;
   const int64_t ch = k.chunk;
   a.groups_per_chan = int32_t(ceil_div(n_out + ch - 1, ch));
-  a.total_groups = n_chans * int64_t(a.groups_per_chan);
+  // cost of a channel's ends in groups (see the kernel): priming block + window fill in front,
+  // and the generic blocks (about 2.5x the time of a fast one) at either recording edge;
+  // measured with scripts/filter_timeline.py: 11.6 groups at the cfg2 shape (2 groups per
+  // block), 33 at cfg3 (5), 7 at cfg4 (1)
+  const int gpb = k.priming_groups;
+  const int edge_end = 2 * gpb;
+  a.edge_start = s.variant & 4 ? 0 : 2 * gpb + 2 + edge_end;
+  a.edge_total = s.variant & 4 ? 0 : a.edge_start + edge_end;
+  a.total_groups = n_chans * int64_t(a.groups_per_chan + a.edge_total);
   a.pad = 0;
+  a.timeline = timeline;
   memset(a.consts, 0, sizeof(a.consts));
   if (s.es == 8) {
     const double v[2] = {-1.0 / double(s.n_taps), 1.7976931348623157e308};
@@ -394,7 +406,8 @@ int launch_comb_e(const CombEShape& s, const void* d_x, void* d_out, const int32
   // register rings stays a small fraction of the work
   const int64_t resident = int64_t(kNumSMs) * k.ctas_per_sm;
   const int64_t min_groups = int64_t(4) * k.priming_groups;
-  const int64_t grid = max64(1, min64(resident, a.total_groups / min_groups));
+  const int64_t grid =
+      max64(1, min64(resident, n_chans * int64_t(a.groups_per_chan) / min_groups));
   void* params[] = {&a};
   const CUresult cr = driver()->LaunchKernel(k.fn, unsigned(grid), 1, 1, unsigned(k.threads), 1, 1,
                                              unsigned(k.smem_bytes), stream, params, nullptr);

@@ -16,6 +16,8 @@ struct FilterTuning {
   int steps_per_chunk;  // U
   int prefetch_chunks;  // chunks in flight beyond the window
   int ctas_per_sm;
+  int variant;          // source variant for A/B measurements (PE_VARIANT)
+  unsigned long long timeline;  // device pointer of the per-CTA timeline (variant bit 1), or 0
 };
 
 struct CombEShape {
@@ -25,7 +27,7 @@ struct CombEShape {
   int n_plus, n_minus;
   const int32_t *plus, *minus;
   int centre, n_taps, w_lo, w_hi, back, fwd;
-  int u, pf, ctas, smem_bytes;
+  int u, pf, ctas, smem_bytes, variant;
 };
 
 bool comb_e_shape(const FilterPlanHeader* hdr, const int32_t* terms, int dtype,
@@ -37,6 +39,6 @@ int launch_comb_e(const CombEShape& s, const void* d_x, void* d_out, const int32
                   const int32_t* d_count, const double* d_recip,
                   int64_t ld_x, int64_t x_t0, int64_t n_x, int64_t ld_out, int64_t t0,
                   int64_t n_out, int64_t n_total, int64_t n_chans, cudaStream_t stream,
-                  int* regs_out);
+                  int* regs_out, unsigned long long timeline = 0);
 
 }  // namespace parrm

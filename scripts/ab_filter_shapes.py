@@ -10,10 +10,10 @@ def taps_of(fs, fa, hw, d):
     return oracle.tap_offsets(p, p / 50, hw, 0, d)
 cases = {"cfg3": taps_of(1000, 145, 2469, "both"), "cfg4": taps_of(30000, 130, 2311, "past"), "cfg2": taps_of(2000, 130, 2000, "both")}
 shapes = {"cfg3": [(64, 1_200_000), (256, 3_600_000)], "cfg4": [(64, 1_200_000), (384, 3_000_000)], "cfg2": [(64, 1_200_000)]}
-tun = {"cfg3": [{}, {"ctas_per_sm": 1}], "cfg4": [{}, {"ctas_per_sm": 1}], "cfg1": [{}, {"steps_per_chunk": 3}],
-       "cfg2": [{}, {"steps_per_chunk": 5}]}
 cases["cfg1"] = oracle.tap_offsets(1.3311148014466094, 0.01, 2000, 20, "both")
 shapes["cfg1"] = [(64, 1_200_000)]
+VARIANTS = [{}, {"variant": 4}]
+tun = {name: VARIANTS for name in ("cfg1", "cfg2", "cfg3", "cfg4")}
 for name, taps in cases.items():
     for (c, n) in shapes[name]:
         d_x = torch.randn((c, n), dtype=torch.float64, device="cuda")
