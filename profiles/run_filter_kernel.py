@@ -19,7 +19,9 @@ gen = torch.Generator(device="cuda").manual_seed(0)
 d_x = torch.randn((n_chans, n_samples), dtype=torch.float64, device="cuda", generator=gen)
 d_y = torch.empty_like(d_x)
 kernel = os.environ.get("PROF_KERNEL")
+tuning = {"variant": int(os.environ["PROF_VARIANT"])} if "PROF_VARIANT" in os.environ else None
 for _ in range(int(os.environ.get("PROF_PASSES", "6"))):
-    engine.filter_device(d_x, taps, d_out=d_y, kernel=None if kernel is None else int(kernel))
+    engine.filter_device(d_x, taps, d_out=d_y, kernel=None if kernel is None else int(kernel),
+                         tuning=tuning)
 torch.cuda.synchronize()
 print("taps", taps.shape[0], "kernel", engine.last_filter_kernel, "checksum", float(d_y.sum()))
