@@ -212,10 +212,11 @@ typedef struct {
   int32_t steps_per_chunk;  /* specialised kernel: comb steps per TMA chunk */
   int32_t prefetch_chunks;  /* specialised kernel: chunks in flight beyond the tap window */
   int32_t ctas_per_sm;      /* specialised kernel: resident CTAs per SM (1 or 2) */
-  int32_t variant;          /* specialised kernel: source variant for A/B measurements (0 = default) */
+  int32_t variant;          /* specialised kernel, measurement aids (0 = default): 2 = record the
+                             * per-CTA timeline, 4 = strips of equal length instead of equal cost */
   int32_t reserved;
   uint64_t timeline;        /* profiling aid, 0 = off: device pointer to 4 uint64 per CTA (SM id,
-                             * start ns, end ns, pieces); written only by variant bit 1 (value 2) */
+                             * start ns, end ns, pieces); written only with variant & 2 */
 } parrm_filter_options_t;
 
 int parrm_filter_apply_ex(const void* d_x, int64_t ld_x, int64_t x_t0, int64_t n_x,

@@ -65,7 +65,8 @@ typedef unsigned long long uintptr_t;
 #define PE_CTAS 2
 #endif
 #ifndef PE_VARIANT
-#define PE_VARIANT 0  // bit mask of source variants kept for A/B measurements (filter options)
+#define PE_VARIANT 0  // filter options: 2 = per-CTA timeline (profiling aid); 4 = strips of
+                      // equal length instead of equal cost (host side, A/B)
 #endif
 
 namespace parrm_e {
@@ -369,7 +370,7 @@ __device__ __forceinline__ int run_block(Rings& r, Walk& w, const Args& a,
           bad_hi = max(bad_hi, g * U + s);
           y = T(0);
         }
-        if (!(PE_VARIANT & 1) || c == threadIdx.x) op[s * D] = y;
+        op[s * D] = y;
       } else if (mode != 0) {
         const int64_t t = Tb + c + int64_t(s) * D;
         T y = mode == 1 ? fma(tot, neg_inv_n, xc) : edge_value(a.count, a.recip, t, a.n_total, xc, tot);
@@ -380,7 +381,7 @@ __device__ __forceinline__ int run_block(Rings& r, Walk& w, const Args& a,
           bad_hi = max(bad_hi, g * U + s);
           y = T(0);
         }
-        if ((!(PE_VARIANT & 1) || c == threadIdx.x) && t >= a.t0 && t < a.t0 + a.n_out) op[s * D] = y;
+        if (t >= a.t0 && t < a.t0 + a.n_out) op[s * D] = y;
       }
     }
     group_end(w, bars, lane, wmask);
@@ -491,14 +492,9 @@ extern "C" __global__ void __launch_bounds__(NT, PE_CTAS) parrm_filter_comb_e(co
     // ------------------------------ consumer warps ------------------------------
     // Lanes past the last chain idle: a half-warp with no active lane costs the shared-memory
     // pipe no wavefront (D = 200: 1 of 14 wavefronts per load instruction of the CTA).
-#if PE_VARIANT & 1  // A/B: the lanes past the last chain shadow it instead
-    const int c = tid < D ? tid : D - 1;
-    const unsigned wmask = 0xffffffffu;
-#else
     if (tid >= D) continue;
     const int c = tid;
     const unsigned wmask = (tid | 31) < D ? 0xffffffffu : ((1u << (D & 31)) - 1u);
-#endif
     for (int i = 0; i < HB + HF; ++i) {   // the window of the first group, except its newest chunk
       mbar_wait(bars + fslot * 8, fphase);
       if (++fslot == Q) {
@@ -538,7 +534,6 @@ extern "C" __global__ void __launch_bounds__(NT, PE_CTAS) parrm_filter_comb_e(co
     fslot = w.fslot;
     fphase = w.fphase;
     for (int k = bad_lo; k <= bad_hi; ++k) {  // rare: re-evaluate the flagged span by the definition
-      if ((PE_VARIANT & 1) && c != tid) break;
       const int64_t t = T0 + c + int64_t(k) * D;
       if (t >= a.t0 && t < a.t0 + a.n_out)
         orow[t] = direct_value(a.taps, a.recip, a.n_total, a.t_max, xrow, t, lo_valid, hi_valid);

@@ -191,6 +191,10 @@ bool comb_e_shape(const FilterPlanHeader* hdr, const int32_t* terms, int dtype,
   auto reg_budget = [&](int ctas) { return std::min(255, (65536 / (ctas * threads)) / 8 * 8); };
   if (ring_regs + 52 > reg_budget(1)) return false;
   int ctas_first = ring_regs + 52 <= reg_budget(2) ? 2 : 1;
+  // float32: half the wavefronts per output, so the step loop is latency-bound and a third CTA
+  // per SM pays where the rings are short (cfg3 shape, float32: 0.62 of its 8 B roofline with
+  // three CTAs and 4 KB chunks, 0.52 with two CTAs and 16 KB; cfg2 / cfg4: no difference)
+  if (s.es == 4 && 3 * threads <= 2048 && ring_regs + 40 <= reg_budget(3)) ctas_first = 3;
   if (tune && tune->ctas_per_sm > 0) ctas_first = tune->ctas_per_sm;
   // chunks in flight beyond the window: 2 measured best wherever more would fit (cfg3 shape,
   // one CTA per SM: 0.637 of the HBM roofline with 2, 0.606 with 4; cfg1 taps: 0.591 / 0.582)
@@ -214,7 +218,7 @@ bool comb_e_shape(const FilterPlanHeader* hdr, const int32_t* terms, int dtype,
     } else {
       for (int cand = s.m[0]; cand >= 1 && u == 0; --cand)  // largest divisor of M0, <= 32 KB
         if (s.m[0] % cand == 0 && int64_t(cand) * s.d * s.es <= 32768 &&
-            int64_t(cand) * s.d * s.es >= 4096 && usable(cand) && smem_for(cand, pf_min) <= budget)
+            int64_t(cand) * s.d >= 512 && usable(cand) && smem_for(cand, pf_min) <= budget)
           u = cand;
       const int u_hi = int(std::max<int64_t>(1, 20480 / (int64_t(s.d) * s.es)));
       for (int cand = u_hi; cand >= 1 && u == 0; --cand)  // largest chunk <= 20 KB that fits

@@ -12,7 +12,7 @@ cases = {"cfg3": taps_of(1000, 145, 2469, "both"), "cfg4": taps_of(30000, 130, 2
 shapes = {"cfg3": [(64, 1_200_000), (256, 3_600_000)], "cfg4": [(64, 1_200_000), (384, 3_000_000)], "cfg2": [(64, 1_200_000)]}
 cases["cfg1"] = oracle.tap_offsets(1.3311148014466094, 0.01, 2000, 20, "both")
 shapes["cfg1"] = [(64, 1_200_000)]
-VARIANTS = [{}, {"variant": 4}]
+VARIANTS = [{}, {"variant": 4}]  # 4 = strips of equal length (the round-2 starting point)
 tun = {name: VARIANTS for name in ("cfg1", "cfg2", "cfg3", "cfg4")}
 for name, taps in cases.items():
     for (c, n) in shapes[name]:

@@ -362,3 +362,28 @@ def test_storage_dtypes_cross_pcie_as_they_are(gpu_engine):
     got = parrm.filter_data(out_dtype=np.float32)
     want = oracle.apply_filter_direct(base.astype(np.int16).astype(np.float64), taps)
     assert got.dtype == np.float32 and rel_err(got.astype(np.float64), want, 1e3) <= RTOL32
+
+
+def test_strip_partition_and_timeline(gpu_engine):
+    """Strips of equal cost (the default) and strips of equal length (``variant`` 4) cover every
+    output exactly once -- bit-identical results on a shape whose channels are shorter than a
+    strip -- and the per-CTA timeline (``variant`` 2 + ``timeline``) records one row per CTA."""
+    import torch
+
+    taps = _case_taps("cfg2")
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((37, 64_123))
+    d_x = torch.from_numpy(x).cuda()
+    base = gpu_engine.filter_device(d_x, taps, kernel=_native.KERNEL_SPECIALISED)
+    assert rel_err(base.cpu().numpy(), oracle.apply_filter_direct(x, taps), np.abs(x).max()) <= 1e-13
+    equal_length = gpu_engine.filter_device(d_x, taps, kernel=_native.KERNEL_SPECIALISED,
+                                            tuning={"variant": 4})
+    assert torch.equal(base, equal_length)
+    timeline = torch.zeros(4 * 1024, dtype=torch.int64, device="cuda")
+    timed = gpu_engine.filter_device(d_x, taps, kernel=_native.KERNEL_SPECIALISED,
+                                     tuning={"variant": 2, "timeline": timeline.data_ptr()})
+    assert torch.equal(base, timed)
+    rows = timeline.cpu().numpy().reshape(-1, 4)
+    rows = rows[rows[:, 2] > 0]
+    assert 1 <= len(rows) <= 2 * 148
+    assert (rows[:, 2] >= rows[:, 1]).all() and (rows[:, 0] < 148).all() and (rows[:, 3] >= 1).all()
