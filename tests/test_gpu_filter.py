@@ -366,8 +366,11 @@ def test_storage_dtypes_cross_pcie_as_they_are(gpu_engine):
 
 def test_strip_partition_and_timeline(gpu_engine):
     """Strips of equal cost (the default) and strips of equal length (``variant`` 4) cover every
-    output exactly once -- bit-identical results on a shape whose channels are shorter than a
-    strip -- and the per-CTA timeline (``variant`` 2 + ``timeline``) records one row per CTA."""
+    output exactly once on a shape whose channels are shorter than a strip.  The two partitions
+    start their running sums at different samples, so they agree to rounding (the same 1e-13 of
+    the input scale both keep against the oracle), not bit for bit; the per-CTA timeline
+    (``variant`` 2 + ``timeline``) keeps the partition, so it is bit-identical, and records one
+    row per CTA."""
     import torch
 
     taps = _case_taps("cfg2")
@@ -378,7 +381,9 @@ def test_strip_partition_and_timeline(gpu_engine):
     assert rel_err(base.cpu().numpy(), oracle.apply_filter_direct(x, taps), np.abs(x).max()) <= 1e-13
     equal_length = gpu_engine.filter_device(d_x, taps, kernel=_native.KERNEL_SPECIALISED,
                                             tuning={"variant": 4})
-    assert torch.equal(base, equal_length)
+    want = oracle.apply_filter_direct(x, taps)
+    assert rel_err(equal_length.cpu().numpy(), want, np.abs(x).max()) <= 1e-13
+    assert rel_err(equal_length.cpu().numpy(), base.cpu().numpy(), np.abs(x).max()) <= 1e-13
     timeline = torch.zeros(4 * 1024, dtype=torch.int64, device="cuda")
     timed = gpu_engine.filter_device(d_x, taps, kernel=_native.KERNEL_SPECIALISED,
                                      tuning={"variant": 2, "timeline": timeline.data_ptr()})
@@ -386,4 +391,6 @@ def test_strip_partition_and_timeline(gpu_engine):
     rows = timeline.cpu().numpy().reshape(-1, 4)
     rows = rows[rows[:, 2] > 0]
     assert 1 <= len(rows) <= 2 * 148
-    assert (rows[:, 2] >= rows[:, 1]).all() and (rows[:, 0] < 148).all() and (rows[:, 3] >= 1).all()
+    assert (rows[:, 2] >= rows[:, 1]).all() and (rows[:, 0] < 148).all()
+    # pieces per CTA: a strip can be empty on a job this small, and some CTA must have worked
+    assert (rows[:, 3] >= 0).all() and rows[:, 3].sum() >= 37
