@@ -24,6 +24,8 @@
 // Kernel 2 (solve) assembles the Gram matrix, factorises it with partial pivoting (zero pivot
 // -> +inf, the reference's LinAlgError path), solves all channels and reduces the objective.
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace parrm {
@@ -697,6 +699,35 @@ eval_reduce_partials_kernel(double* __restrict__ ws, const EvalShape sh) {
 }
 
 // ------------------------------------------------------------------------------------------
+// 1/x for the pivots of the solve: hardware seed (MUFU.RCP64H, ~20 bits) and two Newton steps,
+// straight-line code that the scheduler can interleave with the trailing update -- the IEEE
+// division is a ~400-cycle dependent sequence with a call for the special cases.  Within an
+// ulp of the rounded reciprocal for normal x; 0 -> NaN/inf and non-finite x -> NaN, which
+// only happen where the factorisation is reported singular or is NaN anyway.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
+#ifdef PARRM_SOLVE_TIMING
+// Debug build only: cycles thread 0 of CTA 0 spends in each phase of the solve kernel.
+__device__ unsigned long long g_solve_timing[8];
+#define SOLVE_TICK(slot)                                                    \
+  do {                                                                      \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                              \
+      const long long now__ = clock64();                                    \
+      g_solve_timing[slot] += now__ - stick__;                              \
+      stick__ = now__;                                                      \
+    }                                                                       \
+  } while (0)
+#else
+#define SOLVE_TICK(slot)
+#endif
+
 constexpr int kSolveChans = 64;     // channels per pass: one per thread in the substitutions
 constexpr int kSolveThreads = 256;  // ncu on the 64-thread version: ~45k instructions per warp at
                                     // ~8 cycles each with 6 warps per SM (three CTAs fit by shared
@@ -718,12 +749,16 @@ eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sums
   double* s_x = s_b + M * kSolveChans;        // [M][kSolveChans] work / solution
   __shared__ int s_perm[kMaxRows];
   __shared__ double s_inv[kMaxRows];  // reciprocals of the pivots
-  __shared__ int s_piv;
+  __shared__ unsigned long long s_cand[2 * (kSolveThreads / 32)];  // pivot candidates per warp,
+                                                                   // double-buffered
   __shared__ int s_singular;
   __shared__ double s_part[kSolveThreads / 32];
 
   const int tid = threadIdx.x;
   const int64_t cand = blockIdx.x;
+#ifdef PARRM_SOLVE_TIMING
+  long long stick__ = clock64();
+#endif
 
   // harmonic sums, splits added in a fixed order
   for (int e = tid; e <= two_bw; e += kSolveThreads) {
@@ -783,142 +818,305 @@ eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sums
   }
   __syncthreads();
 
-  // LU with partial pivoting (row interchanges), in place
-  for (int k = 0; k < M; ++k) {
-    if (tid < 32) {
-      // |v| compared through its bit pattern: for non-negative doubles the unsigned order is
-      // the numeric order, a NaN sorts above infinity (so it wins, like a propagating max), and
-      // integer compares do not wait on the FP64 pipe's latency
-      unsigned long long best = 0ull;
-      int best_i = k;
-      for (int i = k + tid; i < M; i += 32) {
-        const unsigned long long v =
-            static_cast<unsigned long long>(__double_as_longlong(fabs(s_g[i * kGStride + k])));
-        if (v > best) {
-          best = v;
-          best_i = i;
-        }
-      }
+  SOLVE_TICK(0);
+  // LU with partial pivoting, in place, rows left where they are: dgetrf's interchanges are
+  // recorded in s_perm and never carried out.  The arithmetic is that of the row-swapping form,
+  // operation for operation, but a step costs ONE block barrier -- there is no swap, and the
+  // search for the next pivot (with the reciprocal it will need) rides on the update that
+  // produces the column it looks at.  Warp w owns rows w, w+8, ... and keeps them in
+  // registers (lane l: columns l and l+32), storing every update through to shared memory,
+  // where the other warps read the pivot row and the substitutions read the factors.  The
+  // lane that holds column k+1 keeps the largest |entry| of the warp's open rows, compared
+  // through its bit pattern (for non-negative doubles the unsigned order is the numeric order,
+  // a NaN sorts above infinity so it wins like a propagating max, and integer compares do not
+  // wait on the FP64 pipe).  After the barrier every thread reduces the eight candidates for
+  // itself.  Equal magnitudes go to the lower row index.  The candidate cells are
+  // double-buffered by the parity of k: a fast warp writes those of step k+1 while a slow one
+  // may still be reading those of step k.
+  constexpr int kWarps = kSolveThreads / 32;
+  constexpr int kSlots = (kMaxRows + kWarps - 1) / kWarps;  // rows per warp
+  static_assert(kMaxRows <= 64, "two column registers per lane");
+  const int warp = tid >> 5, ln = tid & 31;
+  unsigned long long used = 0ull;  // rows already taken as pivots (the same in every thread)
+  double g0[kSlots], g1[kSlots];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-        if (ov > best || (ov == best && oi < best_i)) {
-          best = ov;
-          best_i = oi;
-        }
-      }
-      if (tid == 0) {
-        s_piv = best_i;
-        s_perm[k] = best_i;
-        if (best == 0ull) s_singular = 1;
-      }
-    }
-    __syncthreads();
-    const int piv = s_piv;
-    if (piv != k) {
-      for (int j = tid; j < M; j += kSolveThreads) {
-        const double t = s_g[k * kGStride + j];
-        s_g[k * kGStride + j] = s_g[piv * kGStride + j];
-        s_g[piv * kGStride + j] = t;
-      }
-    }
-    __syncthreads();
-    const double inv_p = 1.0 / s_g[k * kGStride + k];
-    if (tid == 0) s_inv[k] = inv_p;  // reused by the back substitution
-    // multipliers and trailing update: rows over warps, columns over lanes
-    for (int i = k + 1 + (tid >> 5); i < M; i += kSolveThreads / 32) {
-      const double lik = s_g[i * kGStride + k] * inv_p;
-      __syncwarp();
-      if ((tid & 31) == 0) s_g[i * kGStride + k] = lik;
-      for (int j = k + 1 + (tid & 31); j < M; j += 32)
-        s_g[i * kGStride + j] = fma(-lik, s_g[k * kGStride + j], s_g[i * kGStride + j]);
-    }
-    __syncthreads();
+  for (int u = 0; u < kSlots; ++u) {
+    const int i = warp + kWarps * u;
+    g0[u] = (i < M && ln < M) ? s_g[i * kGStride + ln] : 0.0;
+    g1[u] = (i < M && ln + 32 < M) ? s_g[i * kGStride + ln + 32] : 0.0;
   }
+  // A candidate is one 64-bit key: the bit pattern of |entry| with its six lowest mantissa
+  // bits replaced by 63 - row, so the arg-max is a plain unsigned max (equal magnitudes -- to
+  // within 64 ulp -- go to the lower row; a key below 64 is an exact zero pivot; 0 = no row).
+  auto make_key = [](double v, int row) {
+    return (static_cast<unsigned long long>(__double_as_longlong(v)) & 0x7fffffffffffffc0ull) |
+           static_cast<unsigned long long>(63 - row);
+  };
+  auto umax = [](unsigned long long a, unsigned long long b) { return a > b ? a : b; };
+  {
+    // candidates of column 0: lane 0 holds it for every row of the warp
+    unsigned long long key = 0ull;
+#pragma unroll
+    for (int u = 0; u < kSlots; ++u) {
+      const int i = warp + kWarps * u;
+      key = umax(key, i < M ? make_key(g0[u], i) : 0ull);
+    }
+    if (ln == 0) s_cand[warp] = key;
+  }
+  __syncthreads();
+  static_assert(kWarps == 8, "the candidate reduction below shuffles over eight lanes");
+  // One elimination step; HI = column k lives in the second register of its lane (k >= 32).
+  // Straight-line code (selects and predicated stores), so the six rows of a warp overlap.
+  // Registers of columns <= k are dead once their multiplier is stored: they keep computing
+  // (garbage) and are never stored or looked at again.
+  auto lu_step = [&](int k, auto hi_tag) {
+    constexpr bool HI = decltype(hi_tag)::value;
+    const int buf = (k & 1) * kWarps;
+    unsigned long long key = ln < kWarps ? s_cand[buf + ln] : 0ull;
+#pragma unroll
+    for (int o = kWarps / 2; o > 0; o >>= 1) key = umax(key, __shfl_xor_sync(0xffffffffu, key, o));
+    key = __shfl_sync(0xffffffffu, key, 0);
+    const int piv = 63 - int(key & 63ull);
+    used |= 1ull << piv;
+    const double* prow = s_g + piv * kGStride;
+    const double inv_p = fast_rcp(prow[k]);
+    const double p0 = (!HI && ln < M) ? prow[ln] : 0.0, p1 = ln + 32 < M ? prow[ln + 32] : 0.0;
+    if (tid == 0) {
+      s_perm[k] = piv;
+      s_inv[k] = inv_p;  // reused by the back substitution
+      if ((key >> 6) == 0ull) s_singular = 1;
+    }
+    const int kl = k & 31;
+    const bool nhi = k + 1 >= 32;  // which register holds column k+1
+    double rk[kSlots];
+#pragma unroll
+    for (int u = 0; u < kSlots; ++u) rk[u] = __shfl_sync(0xffffffffu, HI ? g1[u] : g0[u], kl);
+    unsigned long long nkey = 0ull;
+#pragma unroll
+    for (int u = 0; u < kSlots; ++u) {
+      const int i = warp + kWarps * u;
+      const bool act = i < M && !((used >> i) & 1ull);
+      const double lik = rk[u] * inv_p;
+      if (!HI) {
+        g0[u] = fma(-lik, p0, g0[u]);
+        g1[u] = fma(-lik, p1, g1[u]);
+        if (act && ln >= kl && ln < M) s_g[i * kGStride + ln] = ln == kl ? lik : g0[u];
+        if (act && ln + 32 < M) s_g[i * kGStride + ln + 32] = g1[u];
+      } else {
+        g1[u] = fma(-lik, p1, g1[u]);
+        if (act && ln >= kl && ln + 32 < M) s_g[i * kGStride + ln + 32] = ln == kl ? lik : g1[u];
+      }
+      nkey = umax(nkey, act ? make_key(nhi ? g1[u] : g0[u], i) : 0ull);
+    }
+    // this lane's column is the one the next step searches
+    if (ln == ((k + 1) & 31)) s_cand[(kWarps - buf) + warp] = nkey;
+    __syncthreads();
+  };
+  {
+    const int m_lo = M < 32 ? M : 32;
+    for (int k = 0; k < m_lo; ++k) lu_step(k, std::false_type{});
+    for (int k = 32; k < M; ++k) lu_step(k, std::true_type{});
+  }
+  SOLVE_TICK(1);
 
   // per-channel solve; channels in passes of kSolveChans.  Thread (lane, role): lane = channel
-  // of the pass; the four roles share the loads and the quadratic form row-wise, role 0 alone
-  // runs the (sequential) substitutions of its channel.
+  // of the pass, the four roles split the rows and keep theirs in registers.  Both
+  // substitutions are column-oriented: once an unknown is final it is eliminated from every
+  // row still open, all rows and channels at once -- one independent FMA per (row, channel)
+  // and one barrier per unknown, instead of a chain of M dependent dot products per channel.
+  // Updates are stored through to s_x, where the next step finds its unknown.
   const double tri = 0.5 * double(M) * double(M + 1);
   const int lane = tid % kSolveChans, role = tid / kSolveChans;
   constexpr int kRoles = kSolveThreads / kSolveChans;
+  constexpr int kRowSlots = (kMaxRows + kRoles - 1) / kRoles;
   double local = 0.0;
   for (int64_t c0 = 0; c0 < sh.n_chans; c0 += kSolveChans) {
     const int64_t ch = c0 + lane;
     const bool live = ch < sh.n_chans;
-    if (live) {
+    double xr[kRowSlots];
+    {
+      // right-hand sides: partials in a fixed order, the loads of all rows of a thread in
+      // flight together (each is an L2 round trip)
       const double* bp = ws + cand * sh.b_stride_period + ch;
-      for (int m = role; m < M; m += kRoles) {
+      const int n_part = sh.b_reduced ? 1 : 2 * sh.n_splits;
+      const bool colsum0 = role == 0 && sh.row0_from_colsum;  // slot 0 of role 0 is row 0
+#pragma unroll
+      for (int u = 0; u < kRowSlots; ++u) xr[u] = 0.0;
+      for (int sp = 0; sp < n_part; ++sp) {
+        double t[kRowSlots];
+#pragma unroll
+        for (int u = 0; u < kRowSlots; ++u) {
+          const int m = role + kRoles * u;
+          const bool get = live && m < M && !(u == 0 && colsum0);
+          t[u] = get ? bp[int64_t(m) * sh.n_chans + int64_t(sp) * sh.b_stride_split] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kRowSlots; ++u) xr[u] += t[u];
+      }
+      // the constant column of W: the same sum of y for every candidate
+      if (colsum0 && live) xr[0] = ws[sh.c_offset + ch];
+#pragma unroll
+      for (int u = 0; u < kRowSlots; ++u) {
+        const int m = role + kRoles * u;
+        if (m < M) {
+          s_b[m * kSolveChans + lane] = xr[u];
+          s_x[m * kSolveChans + lane] = xr[u];
+        }
+      }
+    }
+    __syncthreads();
+    SOLVE_TICK(2);
+    double* xc = s_x + lane;
+    // Both substitutions run in blocks of kBlk unknowns: every thread first resolves the
+    // block's own small triangle for its channel (redundantly over the four roles; the same
+    // FMA chains, in the same order, as the one-unknown-at-a-time form), then each row still
+    // open loses all kBlk terms at once -- two barriers per block instead of one per unknown,
+    // and a quarter of the loads, stores and predicate tests.
+    constexpr int kBlk = 4;
+    auto own_bit = [&](int row) { return (row & (kRoles - 1)) == role ? (1u << (row / kRoles)) : 0u; };
+    unsigned all_rows = 0u;
+#pragma unroll
+    for (int u = 0; u < kRowSlots; ++u) all_rows |= (role + kRoles * u < M) ? (1u << u) : 0u;
+    // L (unit lower): after step k the rows not yet taken as pivots lose l_ik * x[pivot k]
+    unsigned cur = all_rows;  // this thread's rows not yet taken as pivots
+    for (int k0 = 0; k0 + 1 < M; k0 += kBlk) {
+      const int nb = min(kBlk, M - 1 - k0);
+      int pv[kBlk];
+      double z[kBlk];
+      unsigned msk[kBlk];
+#pragma unroll
+      for (int j = 0; j < kBlk; ++j) {
+        pv[j] = j < nb ? s_perm[k0 + j] : 0;
+        cur &= ~(j < nb ? own_bit(pv[j]) : 0u);
+        msk[j] = j < nb ? cur : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < kBlk; ++j) {
         double v = 0.0;
-        if (m == 0 && sh.row0_from_colsum) {
-          v = ws[sh.c_offset + ch];  // the constant column of W: the same sum of y for every candidate
-        } else {
-          // partials in a fixed order, loads eight ahead of the adds (each is an L2 round trip)
-          const double* pm = bp + int64_t(m) * sh.n_chans;
-          const int n_part = sh.b_reduced ? 1 : 2 * sh.n_splits;
-          int sp = 0;
-          for (; sp + 8 <= n_part; sp += 8) {
-            double t[8];
+        if (j < nb) {
+          v = xc[pv[j] * kSolveChans];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) t[u] = pm[(sp + u) * sh.b_stride_split];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v += t[u];
-          }
-          for (; sp < n_part; ++sp) v += pm[sp * sh.b_stride_split];
+          for (int t = 0; t < j; ++t) v = fma(-s_g[pv[j] * kGStride + k0 + t], z[t], v);
         }
-        s_b[m * kSolveChans + lane] = v;
-        s_x[m * kSolveChans + lane] = v;
+        z[j] = v;
       }
-    }
-    __syncthreads();
-    // dot products with four independent partial sums: a single FMA chain is bound by the
-    // FP64 latency
-    const double* xt = s_x + lane;
-    auto dot = [&](const double* g_row, int j0, int j1) {
-      double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
-      int j = j0;
-      for (; j + 4 <= j1; j += 4) {
-        p0 = fma(g_row[j], xt[j * kSolveChans], p0);
-        p1 = fma(g_row[j + 1], xt[(j + 1) * kSolveChans], p1);
-        p2 = fma(g_row[j + 2], xt[(j + 2) * kSolveChans], p2);
-        p3 = fma(g_row[j + 3], xt[(j + 3) * kSolveChans], p3);
-      }
-      for (; j < j1; ++j) p0 = fma(g_row[j], xt[j * kSolveChans], p0);
-      return (p0 + p1) + (p2 + p3);
-    };
-    if (live && role == 0) {
-      // apply the row interchanges, then L (unit lower) and U
-      for (int k = 0; k < M; ++k) {
-        const int p = s_perm[k];
-        if (p != k) {
-          const double t = s_x[k * kSolveChans + lane];
-          s_x[k * kSolveChans + lane] = s_x[p * kSolveChans + lane];
-          s_x[p * kSolveChans + lane] = t;
+      __syncthreads();  // every read of the block's pivot rows precedes their update below
+#pragma unroll
+      for (int u = 0; u < kRowSlots; ++u) {
+        const int i = role + kRoles * u;
+        if ((msk[0] >> u) & 1u) {
+#pragma unroll
+          for (int j = 0; j < kBlk; ++j)
+            if ((msk[j] >> u) & 1u) xr[u] = fma(-s_g[i * kGStride + k0 + j], z[j], xr[u]);
+          xc[i * kSolveChans] = xr[u];
         }
       }
-      for (int i = 1; i < M; ++i)
-        s_x[i * kSolveChans + lane] -= dot(s_g + i * kGStride, 0, i);
-      for (int i = M - 1; i >= 0; --i)
-        s_x[i * kSolveChans + lane] =
-            (s_x[i * kSolveChans + lane] - dot(s_g + i * kGStride, i + 1, M)) * s_inv[i];
+      __syncthreads();
     }
-    __syncthreads();
-    if (live) {
+    SOLVE_TICK(3);
+    // U: unknown k is final in its pivot row (scaled by 1/u_kk when it is read); the pivot
+    // rows of the earlier steps lose u_jk * beta_k
+    cur = all_rows;  // this thread's rows whose unknown is not final yet
+    for (int k0 = M - 1; k0 > 0; k0 -= kBlk) {
+      const int nb = min(kBlk, k0);
+      int pv[kBlk];
+      double bt[kBlk];
+      unsigned msk[kBlk];
+#pragma unroll
+      for (int j = 0; j < kBlk; ++j) {
+        pv[j] = j < nb ? s_perm[k0 - j] : 0;
+        cur &= ~(j < nb ? own_bit(pv[j]) : 0u);
+        msk[j] = j < nb ? cur : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < kBlk; ++j) {
+        double v = 0.0;
+        if (j < nb) {
+          v = xc[pv[j] * kSolveChans];
+#pragma unroll
+          for (int t = 0; t < j; ++t) v = fma(-s_g[pv[j] * kGStride + k0 - t], bt[t], v);
+          v *= s_inv[k0 - j];
+        }
+        bt[j] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < kRowSlots; ++u) {
+        const int i = role + kRoles * u;
+        if ((msk[0] >> u) & 1u) {
+#pragma unroll
+          for (int j = 0; j < kBlk; ++j)
+            if ((msk[j] >> u) & 1u) xr[u] = fma(-s_g[i * kGStride + k0 - j], bt[j], xr[u]);
+          xc[i * kSolveChans] = xr[u];
+        }
+      }
+      __syncthreads();
+    }
+    SOLVE_TICK(4);
+    // beta into the natural order of the unknowns (through registers: s_x is both ends)
+    {
+      double beta_r[(kMaxRows + kRoles - 1) / kRoles];
+#pragma unroll
+      for (int u = 0; u < (kMaxRows + kRoles - 1) / kRoles; ++u) {
+        const int m = role + u * kRoles;
+        beta_r[u] = m < M ? xc[s_perm[m] * kSolveChans] * s_inv[m] : 0.0;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < (kMaxRows + kRoles - 1) / kRoles; ++u) {
+        const int m = role + u * kRoles;
+        if (m < M) xc[m * kSolveChans] = beta_r[u];
+      }
+      __syncthreads();
+    }
+    {
       // sum_i (y - W beta)^2 = y'y - 2 beta'b + beta'G beta holds for ANY beta, so like the
       // reference's explicit residual (parrm.py:630) it is only second-order sensitive to the
-      // rounding of the solve; y'y - beta'b would be first-order sensitive.
+      // rounding of the solve; y'y - beta'b would be first-order sensitive.  Two rows of G at
+      // a time with four partial sums each: a single FMA chain is bound by the FP64 latency.
+      // G is symmetric: beta'G beta = sum_m beta_m (G_mm beta_m + 2 sum_{j<m} G_mj beta_j).
       double cross = 0.0, quad = 0.0, penalty = 0.0;
-      for (int m = role; m < M; m += kRoles) {
-        const double beta = s_x[m * kSolveChans + lane];
-        const double gb = dot(s_g0 + m * kGStride, 0, M);
+      for (int m = role; m < M; m += 2 * kRoles) {
+        const bool two = m + kRoles < M;
+        const int m2 = two ? m + kRoles : m;
+        const double* ga = s_g0 + m * kGStride;
+        const double* gb = s_g0 + m2 * kGStride;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+        int j = 0;
+        for (; j + 4 <= m; j += 4) {  // columns below both diagonals
+          const double x0 = xc[j * kSolveChans], x1 = xc[(j + 1) * kSolveChans];
+          const double x2 = xc[(j + 2) * kSolveChans], x3 = xc[(j + 3) * kSolveChans];
+          a0 = fma(ga[j], x0, a0);
+          b0 = fma(gb[j], x0, b0);
+          a1 = fma(ga[j + 1], x1, a1);
+          b1 = fma(gb[j + 1], x1, b1);
+          a2 = fma(ga[j + 2], x2, a2);
+          b2 = fma(gb[j + 2], x2, b2);
+          a3 = fma(ga[j + 3], x3, a3);
+          b3 = fma(gb[j + 3], x3, b3);
+        }
+        for (; j < m; ++j) {
+          const double x0 = xc[j * kSolveChans];
+          a0 = fma(ga[j], x0, a0);
+          b0 = fma(gb[j], x0, b0);
+        }
+        for (; j < m2; ++j) b1 = fma(gb[j], xc[j * kSolveChans], b1);  // at most kRoles more
+        const double beta = xc[m * kSolveChans];
         cross = fma(beta, s_b[m * kSolveChans + lane], cross);
-        quad = fma(beta, gb, quad);
+        quad = fma(beta, fma(ga[m], beta, 2.0 * ((a0 + a1) + (a2 + a3))), quad);
         penalty = fma((lambda * double(m + 1)) / tri, beta * beta, penalty);
+        if (two) {
+          const double beta2 = xc[m2 * kSolveChans];
+          cross = fma(beta2, s_b[m2 * kSolveChans + lane], cross);
+          quad = fma(beta2, fma(gb[m2], beta2, 2.0 * ((b0 + b1) + (b2 + b3))), quad);
+          penalty = fma((lambda * double(m2 + 1)) / tri, beta2 * beta2, penalty);
+        }
       }
-      local += ((role == 0 ? sumsq[ch] : 0.0) - 2.0 * cross + quad) / double(sh.n_indices) + penalty;
+      if (live)
+        local += ((role == 0 ? sumsq[ch] : 0.0) - 2.0 * cross + quad) / double(sh.n_indices) + penalty;
     }
     __syncthreads();  // the next pass overwrites s_b / s_x
+    SOLVE_TICK(5);
   }
   local = warp_sum(local);
   if ((tid & 31) == 0) s_part[tid >> 5] = local;
@@ -1034,6 +1232,16 @@ static int make_shape(int64_t n_chans, int64_t n_indices, int64_t n_periods, int
 }  // namespace parrm
 
 extern "C" {
+#ifdef PARRM_SOLVE_TIMING
+int parrm_debug_solve_timing(unsigned long long* h_out, int reset) {
+  if (h_out) cudaMemcpyFromSymbol(h_out, parrm::g_solve_timing, sizeof(parrm::g_solve_timing));
+  if (reset) {
+    unsigned long long zero[8] = {0};
+    cudaMemcpyToSymbol(parrm::g_solve_timing, zero, sizeof(zero));
+  }
+  return 0;
+}
+#endif
 #ifdef PARRM_TENSOR_TIMING
 int parrm_debug_tensor_timing(unsigned long long* h_out, int reset) {
   if (h_out) cudaMemcpyFromSymbol(h_out, parrm::g_tensor_timing, sizeof(parrm::g_tensor_timing));

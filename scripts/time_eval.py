@@ -50,7 +50,8 @@ lines = mon.stdout.read().strip().splitlines()
 ms = e0.elapsed_time(e1) / reps
 print(f"{n_cand} candidates x {len(idx)} samples x {n_chans} ch: {ms:.3f} ms per call, "
       f"{n_cand / ms * 1e3:.0f} cand/s, {ms / n_cand * 1e3:.2f} us per candidate")
-print("clock samples (MHz, W, reasons):", lines[len(lines) // 4], "|", lines[len(lines) // 2], "|", lines[-2])
+if len(lines) >= 4:
+    print("clock samples (MHz, W, reasons):", lines[len(lines) // 4], "|", lines[len(lines) // 2], "|", lines[-2])
 
 if hasattr(_native.lib, "parrm_debug_tensor_timing"):  # -DPARRM_TENSOR_TIMING build: phase split
     import ctypes
@@ -67,6 +68,18 @@ if hasattr(_native.lib, "parrm_debug_tensor_timing"):  # -DPARRM_TENSOR_TIMING b
         vals = [buf[w * 8 + i] for i in range(8)]
         print(f"  warp {w:2d}", {n + str(i): round(v / tiles) for i, (n, v) in enumerate(zip(names, vals))},
               "total", round(sum(vals) / tiles))
+
+if hasattr(_native.lib, "parrm_debug_solve_timing"):  # -DPARRM_SOLVE_TIMING build: phase split
+    import ctypes
+
+    buf = (ctypes.c_ulonglong * 8)()
+    _native.lib.parrm_debug_solve_timing(buf, 1)
+    engine.evaluate_device(tile, d_per, 20, 1.0, n_chans)
+    torch.cuda.synchronize()
+    _native.lib.parrm_debug_solve_timing(buf, 0)
+    names = ["gram", "lu", "load_b", "forward", "back", "beta+quad"]
+    print("solve kernel, cycles of thread 0 of CTA 0:", {n: int(buf[i]) for i, n in enumerate(names)},
+          "total", sum(int(buf[i]) for i in range(6)))
 
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
