@@ -335,11 +335,14 @@ def timed_api_passes(dist, fn, steps):
 
     barrier(dist)
     t0 = time.perf_counter()
+    marks = [t0]
     for _ in range(steps):
         out = fn()
+        marks.append(time.perf_counter())
     torch.cuda.synchronize()
     seconds = max_over_ranks(dist, time.perf_counter() - t0)
     barrier(dist)
+    timed_api_passes.last_pass_ms = [round(1e3 * (b - a), 2) for a, b in zip(marks, marks[1:])]
     return seconds, out
 
 
@@ -406,14 +409,20 @@ def run_b200(args):
         for _ in range(min(args.warmup, 3)):
             parrm.filter_data()
         e2e_steps = max(3, min(args.steps, 20))
-        # two back-to-back windows of e2e_steps passes, both reported; the line's e2e is the
-        # faster one (the path is bound by the host's PCIe / memory system, which this process
-        # shares with whatever else runs on the box: one run here saw 18.6 ms where every
-        # other saw 13.6-13.8)
-        e2e_windows = []
-        for _ in range(2):
+        # back-to-back windows of e2e_steps passes, all reported; the line's e2e is the fastest
+        # one.  The path is bound by the host's PCIe / memory system, which this process shares
+        # with whatever else runs on the box (windows of 16.7 and 54.9 ms were seen on one box
+        # where every other gave 13.6-13.8; scripts/e2e_sampler_check.py shows the NVML sampler
+        # is not the cause), so windows repeat -- at most five -- until the two fastest agree
+        # within 3 %.
+        e2e_windows, e2e_passes = [], []
+        for _ in range(5):
             seconds, out = timed_api_passes(dist, parrm.filter_data, e2e_steps)
             e2e_windows.append(seconds)
+            e2e_passes.append(timed_api_passes.last_pass_ms)
+            best = sorted(e2e_windows)
+            if len(best) >= 2 and best[1] <= 1.03 * best[0]:
+                break
         e2e_seconds = min(e2e_windows)
         assert tuple(parrm.filter_shard) == (c0, c1, 0, N_SAMPLES)
 
@@ -472,6 +481,7 @@ def run_b200(args):
             "h2d_bytes_per_step": units * 8, "d2h_bytes_per_step": units * 8,
             "steps": e2e_steps, "ms_per_step": 1e3 * e2e_seconds / e2e_steps,
             "windows_ms_per_step": [round(1e3 * w / e2e_steps, 3) for w in e2e_windows],
+            "slowest_window_pass_ms": e2e_passes[int(np.argmax(e2e_windows))],
             "api": ("PARRM.filter_data() under enable_sharding(gather='none'); this rank's rows "
                     "page-locked in place with pin_array()" if world > 1 else
                     "PARRM.filter_data() on a pinned NumPy array, NumPy result"),

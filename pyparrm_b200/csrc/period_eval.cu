@@ -686,6 +686,13 @@ eval_reduce_partials_kernel(double* __restrict__ ws, const EvalShape sh) {
   for (int64_t ch = threadIdx.x; ch < sh.n_chans; ch += 64) {
     double v = 0.0;
     int sp = 0;
+    for (; sp + 32 <= n_part; sp += 32) {  // every load is an L2 round trip: many in flight,
+      double t[32];                        // the adds in the fixed order all the same
+#pragma unroll
+      for (int u = 0; u < 32; ++u) t[u] = pm[(sp + u) * sh.b_stride_split + ch];
+#pragma unroll
+      for (int u = 0; u < 32; ++u) v += t[u];
+    }
     for (; sp + 8 <= n_part; sp += 8) {
       double t[8];
 #pragma unroll
