@@ -411,12 +411,14 @@ def run_b200(args):
         e2e_steps = max(3, min(args.steps, 20))
         # back-to-back windows of e2e_steps passes, all reported; the line's e2e is the fastest
         # one.  The path is bound by the host's PCIe / memory system, which this process shares
-        # with whatever else runs on the box (windows of 16.7 and 54.9 ms were seen on one box
-        # where every other gave 13.6-13.8; scripts/e2e_sampler_check.py shows the NVML sampler
-        # is not the cause), so windows repeat -- at most five -- until the two fastest agree
-        # within 3 %.
+        # with whatever else runs on the box, so windows repeat -- at most five -- until the two
+        # fastest agree within 3 %.  (A result kept alive across windows makes the next window
+        # page-lock a third 614 MB result buffer, ~0.5 s once: the [14.2, 40.3, 14.2] ms pattern
+        # of earlier runs.  The previous result is dropped first.)
         e2e_windows, e2e_passes = [], []
+        out = None
         for _ in range(5):
+            out = None
             seconds, out = timed_api_passes(dist, parrm.filter_data, e2e_steps)
             e2e_windows.append(seconds)
             e2e_passes.append(timed_api_passes.last_pass_ms)

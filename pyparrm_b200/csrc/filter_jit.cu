@@ -187,10 +187,11 @@ bool comb_e_shape(const FilterPlanHeader* hdr, const int32_t* terms, int dtype,
   // without a usable divisor, the largest chunk up to 20 KB.  A chunk is a whole number of
   // 16-byte units.
   const int ring_regs = (s.m[0] + (s.nk > 1 ? s.m[1] : 0)) * (s.es / 4);
-  const int threads = ((s.d + 31) / 32) * 32 + 32;
-  auto reg_budget = [&](int ctas) { return std::min(255, (65536 / (ctas * threads)) / 8 * 8); };
-  if (ring_regs + 52 > reg_budget(1)) return false;
-  int ctas_first = ring_regs + 52 <= reg_budget(2) ? 2 : 1;
+  const int threads = pattern_first_threads(s.d);
+  auto reg_budget = [&](int ctas) { return pattern_first_reg_budget(s.d, ctas); };
+  // (the planner proposes only plans inside this limit: pattern_first_max_ring)
+  if (ring_regs + kPatternFirstStepRegs > reg_budget(1)) return false;
+  int ctas_first = ring_regs + kPatternFirstStepRegs <= reg_budget(2) ? 2 : 1;
   // float32: half the wavefronts per output, so the step loop is latency-bound and a third CTA
   // per SM pays where the rings are short (cfg3 shape, float32: 0.62 of its 8 B roofline with
   // three CTAs and 4 KB chunks, 0.52 with two CTAs and 16 KB; cfg2 / cfg4: no difference)

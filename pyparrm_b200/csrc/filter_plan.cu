@@ -116,8 +116,8 @@ bool exact(const CombPlan& p, const std::vector<uint8_t>& bit, int lo, int hi) {
 // Searches comb decompositions over strides d_lo..d_hi under the cost model of the run-time
 // specialised kernel (filter_comb_e.cuh): loads per output = number of terms, whatever the
 // number of box lengths, and the two box lengths together must fit the register rings
-// (max_ring values per chain).
-bool best_comb(const int32_t* taps, int n, int d_lo, int d_hi, int max_ring, CombPlan* best) {
+// (pattern_first_max_ring values of `es` bytes per chain at that stride).
+bool best_comb(const int32_t* taps, int n, int d_lo, int d_hi, int es, CombPlan* best) {
   const int lo = std::min(taps[0], 0), hi = std::max(taps[n - 1], 0);
   const int64_t span = int64_t(hi) - lo + 1;
   if (n < 8 || span > (1 << 20)) return false;
@@ -163,10 +163,29 @@ bool best_comb(const int32_t* taps, int n, int d_lo, int d_hi, int max_ring, Com
       }
     }
     std::sort(lengths.rbegin(), lengths.rend());
-    const int n_len = std::min<int>(6, int(lengths.size()));
+    // what the kernel can keep in registers at this stride (a wide stride is a wide CTA)
+    const int max_ring = pattern_first_max_ring(d, es);
+    if (max_ring < 2) continue;
+    // candidate box lengths: the progressions' own lengths and, where those do not fit the
+    // rings, halves and thirds of them (two or three boxes per progression)
+    std::vector<int> cand;
+    auto add_len = [&](int len) {
+      if (len >= 2 && len <= max_ring && std::find(cand.begin(), cand.end(), len) == cand.end())
+        cand.push_back(len);
+    };
+    for (size_t i = 0; i < lengths.size() && i < 6; ++i) add_len(lengths[i].second);
+    for (size_t i = 0; i < lengths.size() && i < 3 && cand.size() < 8; ++i) {
+      const int len = lengths[i].second;
+      if (len > max_ring || 2 * len > max_ring) {
+        add_len((len + 1) / 2);
+        add_len((len + 2) / 3);
+      }
+    }
+    const int n_len = int(cand.size());
     for (int i = 0; i < n_len; ++i) {
       for (int j = i; j < n_len; ++j) {
-        int m[2] = {lengths[i].second, lengths[j].second};
+        int m[2] = {cand[i], cand[j]};
+        if (i != j && m[0] + m[1] > max_ring) continue;
         CombPlan p;
         if (!cover(bit, lo, hi, d, i == j ? 1 : 2, m, &p)) continue;
         if (p.n_terms() > kMaxTerms) continue;
@@ -262,7 +281,7 @@ int parrm_filter_plan(const int32_t* h_taps, int32_t n_taps, int dtype, int stra
 
   CombPlan best;
   const bool ok = best_comb(h_taps, n_taps, kPatternFirstMinStride, kPatternFirstMaxStride,
-                            kPatternFirstMaxRing, &best);
+                            dtype == PARRM_F64 ? 8 : 4, &best);
   const bool worth = ok && (strategy == PARRM_PLAN_COMB || best.cost < 0.6 * double(n_taps));
   if (!worth) {
     if (strategy == PARRM_PLAN_COMB) {

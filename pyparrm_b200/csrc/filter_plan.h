@@ -66,5 +66,21 @@ static_assert(sizeof(FilterPlanHeader) == 128, "plan header is 128 bytes");
 constexpr int kPatternFirstMinStride = 64;
 constexpr int kPatternFirstMaxStride = 992;
 constexpr int kPatternFirstMaxRing = 60;   // M0 + M1
+constexpr int kPatternFirstStepRegs = 52;  // registers a step needs besides the rings
+
+// Threads of the specialised kernel's CTA (one per chain, whole warps, plus the producer warp)
+// and the registers each may use with `ctas` CTAs resident per SM.
+inline int pattern_first_threads(int d) { return ((d + 31) / 32) * 32 + 32; }
+inline int pattern_first_reg_budget(int d, int ctas) {
+  const int r = (65536 / (ctas * pattern_first_threads(d))) / 8 * 8;
+  return r < 255 ? r : 255;
+}
+// Longest rings (M0 + M1 pattern values of `es` bytes per chain) the kernel can hold in
+// registers at stride d: a wide stride is a wide CTA, which leaves few registers per thread.
+// The planner only proposes plans inside this limit, so that what it returns is runnable.
+inline int pattern_first_max_ring(int d, int es) {
+  const int ring = (pattern_first_reg_budget(d, 1) - kPatternFirstStepRegs) / (es / 4);
+  return ring < kPatternFirstMaxRing ? ring : kPatternFirstMaxRing;
+}
 
 }  // namespace parrm

@@ -80,6 +80,42 @@ def test_baseline_configs_get_short_plans():
         assert desc["kind"] == 1 and 64 <= desc["stride"] <= 992 and n_terms <= most
 
 
+RUNNABLE_CASES = CASES + [
+    (1.3311148014466094, None, 2408, 0, "both"),  # the bundled example, create_filter() defaults
+    (8.6613, None, 5000, 0, "both"),              # long windows on a stride of 537
+    (2000 / 130, 1.0, 2000, 0, "both"),           # runs of consecutive taps
+    (30000 / 130, 20.0, 5000, 0, "past"),
+    (7.3, 0.5, 300, 5, "future"),
+]
+
+
+@pytest.mark.parametrize("case", RUNNABLE_CASES)
+def test_comb_plans_are_runnable(case):
+    """Whatever comb plan the planner returns, the specialised kernel must accept: the planner
+    bounds the box lengths by the registers the kernel has at that stride (a stride of 800 is an
+    832-thread CTA: 72 registers per thread, rings of at most ten float64 values), instead of
+    returning the cheapest plan and leaving the job to the tap-by-tap gather."""
+    period, phw, hw, omit, direction = case
+    taps = oracle.tap_offsets(period, period / 50 if phw is None else phw, hw, omit, direction)
+    for dtype in (_native.F64, _native.F32):
+        plan, desc = _native.plan_filter(taps, dtype)
+        if desc["kind"] != 1:
+            continue
+        shape = np.zeros(12, dtype=np.int32)
+        status = _native.lib.parrm_filter_specialise_check(plan.ctypes.data, dtype, None,
+                                                           shape.ctypes.data, None)
+        assert status == 0, (case, dtype, desc["stride"], desc["windows"], _native.last_error())
+        if case in CASES and dtype == _native.F64:
+            continue  # expanded in test_plans_are_exact_regroupings
+        lo, hi = min(int(taps[0]), 0), max(int(taps[-1]), 0)
+        want = np.zeros(hi - lo + 1, dtype=np.int64)
+        want[taps - lo] = 1
+        assert np.array_equal(expand(desc, lo, hi), want)
+    # the BASELINE tap sets and the five realistic ones added above must not end on the gather
+    if case in CASES[:5] or case in RUNNABLE_CASES[len(CASES):]:
+        assert _native.plan_filter(taps, _native.F64)[1]["kind"] == 1, case
+
+
 def test_random_tap_sets():
     rng = np.random.default_rng(7)
     for _ in range(40):
