@@ -887,6 +887,31 @@ def bench_search(engine, dist, world, rank, args):
                      "flops_per_candidate": flops_per_cand,
                      "reference_flops_per_candidate": reference_flops_per_cand},
     }
+    if world == 1:
+        # the search's "fp32" mode (PARRM(precision="fp32")): float32 storage of the tile, widened
+        # once per call, the fit on the same FP64 tensor path -- same flops, same roofline
+        (tile32,) = engine.prepare_tiles(data, [indices], 3.0, "fp32")
+        d_per = torch.from_numpy(periods).cuda()
+        err64 = engine.evaluate_device(tile, d_per, bandwidth, 1.0, n_chans)
+        for _ in range(2):
+            err32 = engine.evaluate_device(tile32, d_per, bandwidth, 1.0, n_chans)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(steps):
+            err32 = engine.evaluate_device(tile32, d_per, bandwidth, 1.0, n_chans)
+        f1.record(stream)
+        torch.cuda.synchronize()
+        sec32 = f0.elapsed_time(f1) * 1e-3
+        result["fp32_mode"] = {
+            "what": "same candidates on the float32 tile of PARRM(precision='fp32'): float32 storage, "
+                    "widened once per call, fit on the FP64 tensor path (no FP32-pipe kernel: "
+                    "DESIGN.md 4.4)",
+            "value": per_rank * steps / sec32, "unit": "candidates/s",
+            "roofline_frac_of_fp64_peak": flops_per_cand * per_rank * steps / sec32 / 1e12 / fp64_peak,
+            "max_rel_err_vs_fp64_tile": float(((err32 - err64).abs() / err64.abs()).max().item()),
+            "tolerance": 1e-4,
+        }
+        del tile32
     # the whole search through the public API (host array in, period out): three coarse-to-fine
     # grid runs + lock-step Nelder-Mead, ~1 800 objective evaluations; under
     # enable_sharding() every rank uploads only its channel block and evaluates its candidates

@@ -775,7 +775,20 @@ eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sums
     } else {
       const double* tp = ws + sh.t_offset + cand * sh.t_stride_period;
       int sp = 0;
-      for (; sp + 4 <= sh.n_splits; sp += 4) {  // fixed order, loads ahead of the adds
+      for (; sp + 16 <= sh.n_splits; sp += 16) {  // fixed order, loads ahead of the adds
+        double tc[16], ts[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          tc[u] = tp[(sp + u) * sh.t_stride_split + e - 1];
+          ts[u] = tp[(sp + u) * sh.t_stride_split + two_bw + e - 1];
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          c += tc[u];
+          s += ts[u];
+        }
+      }
+      for (; sp + 4 <= sh.n_splits; sp += 4) {
         double tc[4], ts[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
