@@ -389,6 +389,15 @@ def run_b200(args):
         # ---- value: device resident -------------------------------------------------
         for _ in range(args.warmup):
             engine.filter_device(d_x, taps, d_out=d_y)
+        # A pass is 0.25 ms, so W passes are over before a GPU that idled at the rendezvous has
+        # reached its boost clocks (seen as 0.28-0.29 ms per pass on some ranks of an 8-GPU
+        # run, 0.255 on the others): warm up for at least 0.2 s of back-to-back passes.
+        torch.cuda.synchronize()
+        t_warm = time.perf_counter()
+        while time.perf_counter() - t_warm < 0.2:
+            for _ in range(20):
+                engine.filter_device(d_x, taps, d_out=d_y)
+            torch.cuda.synchronize()
         barrier(dist)
         launches0 = engine.launches
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
