@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PARRM_B200_ABI_VERSION 5
+#define PARRM_B200_ABI_VERSION 6
 
 typedef enum {
   PARRM_OK = 0,
@@ -74,6 +74,11 @@ int         parrm_copy_d2h_async(void* h_dst, const void* d_src, size_t bytes, v
  * staged through pinned buffers (PARRM holds `data` by reference, parrm.py:124). */
 int         parrm_host_register(void* h_ptr, size_t bytes);
 int         parrm_host_unregister(void* h_ptr);
+/* Host-to-host copy on up to n_threads threads of a persistent pool, streaming stores for
+ * large pieces: the staged leg of the host pipeline, where a pageable recording (the
+ * reference takes any ndarray, parrm.py:877-886, 120-124) is moved through page-locked
+ * staging buffers.  Blocks until the copy is complete; ranges must not overlap. */
+int         parrm_host_copy(void* h_dst, const void* h_src, size_t bytes, int n_threads);
 
 /* ------------------------------------------------------------------------
  * Standardisation: PARRM._standardise_data (parrm.py:272-280)

@@ -15,7 +15,6 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
-from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 
 import numpy as np
@@ -30,8 +29,7 @@ _SEARCH_CHUNK_BYTES = int(os.environ.get("PYPARRM_B200_SEARCH_CHUNK_MB", "128"))
 _PINNED_OUT_LIMIT = int(os.environ.get("PYPARRM_B200_PINNED_OUT_MB", "2048")) << 20
 _EVAL_WS_LIMIT = int(os.environ.get("PYPARRM_B200_EVAL_WS_MB", "1024")) << 20
 _N_SLOTS = 3
-_COPY_THREADS = max(1, min(8, (os.cpu_count() or 1)))
-_copy_pool: ThreadPoolExecutor | None = None
+_COPY_THREADS = max(1, min(int(os.environ.get("PYPARRM_B200_COPY_THREADS", "8")), (os.cpu_count() or 1)))
 
 
 def _vp(ptr: int) -> ctypes.c_void_p:
@@ -39,23 +37,9 @@ def _vp(ptr: int) -> ctypes.c_void_p:
 
 
 def _threaded_memmove(dst: int, src: int, nbytes: int) -> None:
-    """memcpy between host buffers on several threads (ctypes releases the GIL)."""
-    global _copy_pool
-    piece = 8 << 20
-    if nbytes <= piece or _COPY_THREADS == 1:
-        ctypes.memmove(dst, src, nbytes)
-        return
-    if _copy_pool is None:
-        _copy_pool = ThreadPoolExecutor(max_workers=_COPY_THREADS)
-    n_pieces = min(_COPY_THREADS, -(-nbytes // piece))
-    step = -(-nbytes // n_pieces)
-    step = (step + 63) & ~63
-    futures = []
-    for off in range(0, nbytes, step):
-        n = min(step, nbytes - off)
-        futures.append(_copy_pool.submit(ctypes.memmove, dst + off, src + off, n))
-    for f in futures:
-        f.result()
+    """Host-to-host copy between a pageable array and a pinned staging buffer, on the
+    library's copy threads (``parrm_host_copy``; the call releases the GIL)."""
+    check(lib.parrm_host_copy(_vp(dst), _vp(src), nbytes, _COPY_THREADS), "parrm_host_copy")
 
 
 def pinned_empty(shape, dtype=np.float64) -> np.ndarray:

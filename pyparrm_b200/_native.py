@@ -20,7 +20,7 @@ DIR_BOTH, DIR_PAST, DIR_FUTURE = 0, 1, 2
 DIRECTIONS = {"both": DIR_BOTH, "past": DIR_PAST, "future": DIR_FUTURE}
 MAX_BANDWIDTH = 23
 NM_STATE_BYTES = 88
-ABI_VERSION = 5
+ABI_VERSION = 6
 PLAN_AUTO, PLAN_GATHER, PLAN_COMB = 0, 1, 2
 KERNEL_AUTO, KERNEL_GATHER, KERNEL_SPECIALISED = 0, 1, 3
 
@@ -100,6 +100,7 @@ SIGNATURES = {
     ),
     "parrm_host_register": (c_int, [c_void_p, c_size_t]),
     "parrm_host_unregister": (c_int, [c_void_p]),
+    "parrm_host_copy": (c_int, [c_void_p, c_void_p, c_size_t, c_int]),
     "parrm_convert": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p]),
     "parrm_convert_f64_to_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "parrm_convert_f32_to_f64": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),

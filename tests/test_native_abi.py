@@ -76,3 +76,41 @@ def test_no_silent_cpu_path():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         p.find_period()
     assert _native.device_count() == 0
+
+
+def test_host_copy_is_exact_for_any_size_alignment_and_thread_count():
+    """``parrm_host_copy`` (the staged leg of the host pipeline for pageable arrays): every
+    byte copied, nothing outside the range touched, for odd sizes, unaligned ends, more threads
+    than pieces, and two callers at once (the pool serialises them)."""
+    import ctypes
+    import threading
+
+    lib = _native.lib
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 63, 65, 4097, (1 << 20) + 17, 3 * (1 << 20) + 5, 9_600_007):
+        for off_s, off_d in ((0, 0), (1, 3), (8, 16)):
+            src = rng.integers(0, 255, n + off_s + 64, dtype=np.uint8)
+            for threads in (1, 3, 8, 16):
+                dst = np.full(n + off_d + 64, 7, dtype=np.uint8)
+                assert lib.parrm_host_copy(ctypes.c_void_p(dst.ctypes.data + off_d),
+                                           ctypes.c_void_p(src.ctypes.data + off_s), n, threads) == 0
+                assert np.array_equal(dst[off_d:off_d + n], src[off_s:off_s + n]), (n, threads)
+                assert (dst[:off_d] == 7).all() and (dst[off_d + n:] == 7).all()
+    assert lib.parrm_host_copy(None, None, 5, 2) != 0 and "null" in _native.last_error()
+    assert lib.parrm_host_copy(None, None, 0, 0) != 0  # thread count out of range
+
+    a, b = (rng.integers(0, 255, 6 << 20, dtype=np.uint8) for _ in range(2))
+    out = [np.zeros_like(a), np.zeros_like(b)]
+
+    def worker(i, src):
+        for _ in range(5):
+            out[i][:] = 0
+            assert lib.parrm_host_copy(ctypes.c_void_p(out[i].ctypes.data),
+                                       ctypes.c_void_p(src.ctypes.data), src.nbytes, 4) == 0
+            assert np.array_equal(out[i], src)
+
+    pool = [threading.Thread(target=worker, args=(i, s)) for i, s in enumerate((a, b))]
+    for t in pool:
+        t.start()
+    for t in pool:
+        t.join()
