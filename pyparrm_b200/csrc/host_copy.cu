@@ -9,7 +9,10 @@
 // engine, not by a core, and write-allocate would read every destination line first.
 // Host-only C++; no CUDA calls.
 #include <emmintrin.h>
+#include <pthread.h>
 #include <string.h>
+
+#include <new>
 
 #include <condition_variable>
 #include <mutex>
@@ -109,9 +112,24 @@ class CopyPool {
   int next_ = 0, parts_ = 0, pending_ = 0;
 };
 
+// Never destroyed: its threads are parked for the life of the process.  A forked child has
+// none of the parent's threads, so it starts over with a pool of its own.
+CopyPool* g_pool = nullptr;
+std::mutex g_pool_mutex;
 CopyPool* pool() {
-  static CopyPool* p = new CopyPool();  // never destroyed: its threads outlive static teardown
-  return p;
+  std::lock_guard<std::mutex> g(g_pool_mutex);
+  if (g_pool == nullptr) {
+    static bool hooked = false;
+    if (!hooked) {
+      pthread_atfork(nullptr, nullptr, [] {
+        new (&g_pool_mutex) std::mutex();  // may have been held by a thread that is not here
+        g_pool = nullptr;
+      });
+      hooked = true;
+    }
+    g_pool = new CopyPool();
+  }
+  return g_pool;
 }
 
 }  // namespace

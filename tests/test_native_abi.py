@@ -114,3 +114,12 @@ def test_host_copy_is_exact_for_any_size_alignment_and_thread_count():
         t.start()
     for t in pool:
         t.join()
+
+    # a forked child has none of the parent's copy threads: it must start a pool of its own
+    pid = os.fork()
+    if pid == 0:
+        out[0][:] = 0
+        rc = lib.parrm_host_copy(ctypes.c_void_p(out[0].ctypes.data), ctypes.c_void_p(a.ctypes.data),
+                                 a.nbytes, 4)
+        os._exit(0 if rc == 0 and np.array_equal(out[0], a) else 1)
+    assert os.WEXITSTATUS(os.waitpid(pid, 0)[1]) == 0
