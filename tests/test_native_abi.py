@@ -118,6 +118,9 @@ def test_host_copy_is_exact_for_any_size_alignment_and_thread_count():
     # a forked child has none of the parent's copy threads: it must start a pool of its own
     pid = os.fork()
     if pid == 0:
+        import signal
+
+        signal.alarm(30)  # a deadlocked child must not hang the suite
         out[0][:] = 0
         rc = lib.parrm_host_copy(ctypes.c_void_p(out[0].ctypes.data), ctypes.c_void_p(a.ctypes.data),
                                  a.nbytes, 4)
