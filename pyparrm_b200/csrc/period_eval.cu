@@ -743,7 +743,7 @@ constexpr int kSolveThreads = 256;  // ncu on the 64-thread version: ~45k instru
 constexpr int kGStride = kMaxRows + 2;  // row stride of the Gram matrix: odd, so that the pivot
                                         // search down a column is free of bank conflicts
 
-__global__ void __launch_bounds__(kSolveThreads)
+__global__ void __launch_bounds__(kSolveThreads, 3)
 eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sumsq, double lambda,
                   int64_t n_chans_divisor, double* __restrict__ fit_error, const EvalShape sh) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
