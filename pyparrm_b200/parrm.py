@@ -56,6 +56,12 @@ def _require_number(value, name: str) -> None:
         raise TypeError(f"`{name}` must be an int or a float.")
 
 
+def _is_device_tensor(obj) -> bool:
+    """True for a torch tensor that lives on a CUDA device (without importing torch here)."""
+    return (type(obj).__module__.split(".")[0] == "torch" and hasattr(obj, "is_cuda")
+            and bool(obj.is_cuda))
+
+
 class PARRM:
     """Remove periodic stimulation artefacts with PARRM (Dastin-van Rijn et al., 2021).
 
@@ -509,6 +515,9 @@ class PARRM:
         (first / last samples of a one-sided filter) the result is 0, the documented intent of
         parrm.py:867-869 (the reference's FFT path returns rounding noise there).
 
+        ``data`` may also be a CUDA ``torch.Tensor`` ``[channels, times]`` (additive): it is
+        filtered where it lies and a device tensor comes back -- nothing crosses PCIe.
+
         Under ``pyparrm_b200.enable_sharding()`` every rank filters its channel block (time
         block when channels are fewer than ranks, halos read from the recording); what comes
         back follows the ``gather`` mode given there, and ``filter_shard`` holds the
@@ -520,10 +529,27 @@ class PARRM:
                 "The filter has not yet been created. The `create_filter` method must "
                 "be called first."
             )
-        data = self._check_sort_filter_data_inputs(data)
         half_width = (self._filter.shape[0] - 1) // 2
         taps = (np.flatnonzero(self._filter < 0) - half_width).astype(np.int32)
         engine = _engine.get_engine()
+        if _is_device_tensor(data):
+            # additive overload: a CUDA tensor [channels, times] (float64 or
+            # float32) is filtered where it lies and the result stays on the device -- no PCIe
+            # in either direction; `filtered_data` then holds the device tensor
+            if data.dim() != 2:
+                raise ValueError("`data` must be a 2D array.")
+            if out_dtype is not None:
+                raise TypeError("`out_dtype` applies to NumPy results; convert the returned tensor.")
+            d_x = data if data.stride(1) == 1 else data.contiguous()
+            want = engine.torch.float32 if self._precision == "fp32" else engine.torch.float64
+            if d_x.dtype != want:  # float32 / integer recordings are widened, as on the host path
+                d_x = d_x.to(want)
+            self.filter_shard = (0, d_x.shape[0], 0, d_x.shape[1])
+            self._filtered_data = engine.filter_device(d_x, taps)
+            if self._verbose:
+                print("    ... Data filtered\n")
+            return self._filtered_data
+        data = self._check_sort_filter_data_inputs(data)
         if _sharding.active():
             out, self.filter_shard, _ = _sharding.filter_sharded(
                 engine, data, taps, self._precision, _sharding.gather_mode(), out_dtype)

@@ -135,6 +135,34 @@ def test_device_tensor_entry_point(gpu_engine):
     assert rel_err(d_out.cpu().numpy(), oracle.apply_filter_direct(x, taps), 10) <= 1e-13
 
 
+def test_public_api_accepts_device_tensors(gpu_engine):
+    """``PARRM.filter_data(cuda_tensor)`` (additive overload): filtered on the
+    device, device tensor back, same values as the NumPy path; other non-NumPy inputs keep the
+    reference's TypeError (parrm.py:877-886)."""
+    import torch
+
+    data = make_recording(5, 60_000, 2000, 130, seed=2)
+    parrm = PARRM(data, 2000, 130, verbose=False)
+    parrm._period = np.float64(2000 / 130 * (1 + 3e-6))
+    parrm.create_filter(filter_half_width=2000)
+    want = parrm.filter_data().copy()
+    got = parrm.filter_data(torch.from_numpy(data).cuda())
+    assert isinstance(got, torch.Tensor) and got.is_cuda and got.dtype == torch.float64
+    assert parrm.filtered_data is got
+    assert rel_err(got.cpu().numpy(), want, np.abs(data).max()) <= 1e-13
+    got32 = parrm.filter_data(torch.from_numpy(data.astype(np.float32)).cuda())  # widened
+    assert got32.dtype == torch.float64
+    assert rel_err(got32.cpu().numpy(), want, np.abs(data).max()) <= 1e-6
+    strided = torch.from_numpy(np.ascontiguousarray(data.T)).cuda().T  # not row-major
+    assert rel_err(parrm.filter_data(strided).cpu().numpy(), want, np.abs(data).max()) <= 1e-13
+    with pytest.raises(ValueError, match="must be a 2D array"):
+        parrm.filter_data(torch.zeros(7, device="cuda", dtype=torch.float64))
+    with pytest.raises(TypeError, match="must be a NumPy array"):
+        parrm.filter_data(torch.zeros((2, 7), dtype=torch.float64))  # CPU tensor: reference rule
+    with pytest.raises(TypeError, match="must be a NumPy array"):
+        parrm.filter_data([[1.0, 2.0]])
+
+
 def test_float32_mode(gpu_engine):
     x = make_recording(4, 100_000, 2000, 130, seed=9)
     taps = oracle.tap_offsets(2000 / 130, 0.3, 2000, 0, "both")
