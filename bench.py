@@ -389,15 +389,17 @@ def run_b200(args):
         # ---- value: device resident -------------------------------------------------
         for _ in range(args.warmup):
             engine.filter_device(d_x, taps, d_out=d_y)
-        # A pass is 0.25 ms, so W passes are over before a GPU that idled at the rendezvous has
-        # reached its boost clocks (seen as 0.28-0.29 ms per pass on some ranks of an 8-GPU
-        # run, 0.255 on the others): warm up for at least 0.2 s of back-to-back passes.
+        # A pass is 0.25 ms: W passes are over before a GPU that idled at the rendezvous is at
+        # its boost clocks (ranks that waited ran 0.28-0.29 ms per pass for the whole region,
+        # the others 0.255), while 50 ms or more of back-to-back passes put the GPU at its power
+        # cap (0.265-0.275 ms; scripts/warmup_sweep.py: 2-20 ms of warm-up give 0.2475).  So:
+        # rendezvous, 10 ms of passes with every rank in step, rendezvous again (immediate),
+        # then the timed region -- the burst condition the measured HBM peak was taken under.
+        # The power-capped rate is measured separately below (roofline.sustained).
+        barrier(dist)
+        for _ in range(40):
+            engine.filter_device(d_x, taps, d_out=d_y)
         torch.cuda.synchronize()
-        t_warm = time.perf_counter()
-        while time.perf_counter() - t_warm < 0.2:
-            for _ in range(20):
-                engine.filter_device(d_x, taps, d_out=d_y)
-            torch.cuda.synchronize()
         barrier(dist)
         launches0 = engine.launches
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -411,6 +413,20 @@ def run_b200(args):
         dev_seconds = max_over_ranks(dist, start.elapsed_time(stop) * 1e-3)
         kernel_seconds = start.elapsed_time(stop) * 1e-3 / args.steps  # one launch per step
         rank_ms = [round(1e3 * v, 4) for v in all_ranks(dist, kernel_seconds)]
+
+        # the same pass after half a second of back-to-back passes: the GPU at its power cap
+        t_hot = time.perf_counter()
+        while time.perf_counter() - t_hot < 0.5:
+            for _ in range(40):
+                engine.filter_device(d_x, taps, d_out=d_y)
+            torch.cuda.synchronize()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record(stream)
+        for _ in range(50):
+            engine.filter_device(d_x, taps, d_out=d_y)
+        h1.record(stream)
+        torch.cuda.synchronize()
+        sustained_seconds = max_over_ranks(dist, h0.elapsed_time(h1) * 1e-3 / 50)
 
         standardise = bench_standardise(engine, d_x, hbm_peak) if world == 1 else None
 
@@ -503,6 +519,12 @@ def run_b200(args):
             "frac": achieved / hbm_peak, "traffic": traffic,
             "kernel": filter_kernel, "peak_source": peak_source,
             "algorithmic_bytes_per_launch": BYTES_PER_CHANNEL_SAMPLE * units,
+            "sustained": {
+                "ms_per_step": 1e3 * sustained_seconds,
+                "frac": BYTES_PER_CHANNEL_SAMPLE * units / sustained_seconds / 1e9 / hbm_peak,
+                "what": "the same launch after 0.5 s of back-to-back passes (GPU at its power cap: "
+                        "sw_power_cap), max over ranks, against the same burst copy peak",
+            },
         },
         "parity_max_rel_err": max(parity, dev_parity),
         "find_period": search,
