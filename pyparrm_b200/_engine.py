@@ -643,14 +643,25 @@ class DeviceEngine:
         return data, code
 
     # A job of at least this many channel-samples gets the kernel specialised for its plan
-    # (built once per plan, ~1 s); smaller one-off jobs keep the pre-built kernels.
+    # (built once per plan and device: ~0.5 s for the BASELINE tap sets); smaller one-off jobs
+    # keep the pre-built kernels.  The build time grows faster than the unrolled step loop
+    # (terms x box length loads per block: cfg2 200, 0.5 s; 860 taps in runs of 41: 1 764,
+    # 22 s), so the job size that pays for it grows with the square of that.
     SPECIALISE_FROM = 1 << 24
 
-    def _filter_options(self, job_samples: int, kernel=None, tuning=None):
+    def _specialise_from(self, h_plan) -> int:
+        info = np.zeros(16, dtype=np.int32)
+        check(lib.parrm_filter_plan_info(_vp(h_plan.ctypes.data), _vp(info.ctypes.data), None, 0),
+              "parrm_filter_plan_info")
+        work = int(info[14]) * max(int(info[3]), int(info[4]), 1)  # terms x longest box
+        return int(self.SPECIALISE_FROM * max(1.0, work / 400.0) ** 2)
+
+    def _filter_options(self, job_samples: int, kernel=None, tuning=None, h_plan=None):
         opts = _native.FilterOptions()
         if kernel is None:
             kernel = int(os.environ.get("PYPARRM_B200_FILTER_KERNEL", _native.KERNEL_AUTO))
-            if kernel == _native.KERNEL_AUTO and job_samples >= self.SPECIALISE_FROM:
+            threshold = self.SPECIALISE_FROM if h_plan is None else self._specialise_from(h_plan)
+            if kernel == _native.KERNEL_AUTO and job_samples >= threshold:
                 kernel = -1  # specialise when the plan allows, else whatever AUTO picks
         opts.kernel = _native.KERNEL_AUTO if kernel == -1 else int(kernel)
         opts.try_special = kernel == -1
@@ -686,7 +697,7 @@ class DeviceEngine:
         if d_out is None:
             d_out = t.empty((n_chans, n_samples), dtype=d_x.dtype, device=d_x.device)
         stream = stream or t.cuda.current_stream()
-        opts = self._filter_options(n_chans * n_samples, kernel, tuning)
+        opts = self._filter_options(n_chans * n_samples, kernel, tuning, h_plan)
         for c0 in range(0, n_chans, 65535):
             c1 = min(c0 + 65535, n_chans)
             self._apply(
@@ -714,7 +725,7 @@ class DeviceEngine:
             if f32:
                 d_x = d_x.to(t.float32)
             d_out = t.empty((n_chans, t1 - t0), dtype=d_x.dtype, device=self.device)
-            opts = self._filter_options(n_chans * (t1 - t0))
+            opts = self._filter_options(n_chans * (t1 - t0), h_plan=h_plan)
             for c0 in range(0, n_chans, 65535):
                 c1 = min(c0 + 65535, n_chans)
                 self._apply(
@@ -752,7 +763,7 @@ class DeviceEngine:
             return out
         with self._lock, t.cuda.device(self.device):
             h_plan, d_plan, (w_lo, w_hi) = self._plan(taps, comp_code, strategy)
-            opts = self._filter_options(n_chans * n_samples)
+            opts = self._filter_options(n_chans * n_samples, h_plan=h_plan)
             span = w_hi - w_lo
             row_bytes = n_samples * max(es_in, es_out)
             # chunk list: (c0, c1, t0, t1, x0, x1) -- channels [c0,c1), outputs [t0,t1), inputs [x0,x1)

