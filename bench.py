@@ -596,21 +596,25 @@ def bench_e2e_variants(engine, data, taps, steps, period):
         p.create_filter(filter_half_width=HALF_WIDTH, filter_direction="both")
         for _ in range(2):
             p.filter_data(**kw)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            p.filter_data(**kw)
-        torch.cuda.synchronize()
-        seconds = time.perf_counter() - t0
+        windows = []
+        for _ in range(2):  # two windows, the faster one reported (host-bound: noisy)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                p.filter_data(**kw)
+            torch.cuda.synchronize()
+            windows.append(time.perf_counter() - t0)
+        seconds = min(windows)
         return {"value": array.size * steps / seconds, "unit": "channel-samples/s",
-                "ms_per_step": 1e3 * seconds / steps}
+                "ms_per_step": 1e3 * seconds / steps,
+                "windows_ms_per_step": [round(1e3 * w / steps, 2) for w in windows]}
 
     out = {}
     pageable = np.array(data)  # ordinary malloc'ed copy, as np.load would hand over
     out["pageable_f64"] = dict(rate(pageable), h2d_bytes_per_step=data.size * 8,
                                d2h_bytes_per_step=data.size * 8,
                                what="pageable float64 in (staged through pinned buffers by "
-                                    "8 copy threads), float64 out")
+                                    "parrm_host_copy, 8 threads), float64 out")
     t0 = time.perf_counter()
     handle = pin_array(pageable)
     register_ms = 1e3 * (time.perf_counter() - t0)

@@ -15,7 +15,7 @@ if [ "${BENCH:-1}" = "1" ]; then
   echo "reference rc=$?"; tail -c 800 gpurun_out/bench_reference.log
 fi
 if [ "${LAUNCHES:-1}" = "1" ]; then
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv \
     --log-file gpurun_out/bench_launch_list.csv python bench.py --steps 5 --warmup 3 \
     > gpurun_out/ncu_bench.log 2>&1
   echo "ncu rc=$?"
