@@ -519,7 +519,8 @@ class PARRM:
         parrm.py:867-869 (the reference's FFT path returns rounding noise there).
 
         ``data`` may also be a CUDA ``torch.Tensor`` ``[channels, times]`` (additive): it is
-        filtered where it lies and a device tensor comes back -- nothing crosses PCIe.
+        filtered where it lies and a device tensor comes back -- nothing crosses PCIe (and
+        nothing is sharded: under ``enable_sharding()`` the tensor is this rank's own).
 
         Under ``pyparrm_b200.enable_sharding()`` every rank filters its channel block (time
         block when channels are fewer than ranks, halos read from the recording); what comes
