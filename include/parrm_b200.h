@@ -235,7 +235,9 @@ const char* parrm_filter_last_kernel(void);
 /* Builds the specialised kernel for a plan WITHOUT loading or launching it (works on a host
  * with no GPU): the build check of the run-time compiled path.  shape[0..11] (may be NULL) =
  * stride, box kinds, M0, M1, boxes of M0, boxes of M1, single taps, steps per chunk, chunks
- * in flight, CTAs per SM, dynamic shared memory bytes, threads per CTA.
+ * in flight, CTAs per SM, dynamic shared memory bytes, threads per CTA.  With cubin_bytes
+ * NULL only the shape is worked out (is the plan inside the kernel's range?) and nothing is
+ * compiled; otherwise *cubin_bytes receives the size of the compiled image.
  * PARRM_ERR_UNSUPPORTED: plan outside the kernel's range, or NVRTC not available. */
 int parrm_filter_specialise_check(const void* h_plan, int dtype,
                                   const parrm_filter_options_t* options, int32_t* shape,

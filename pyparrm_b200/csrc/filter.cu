@@ -265,6 +265,7 @@ int parrm_filter_specialise_check(const void* h_plan, int dtype,
                            s.u, s.pf, s.ctas, s.smem_bytes, ((s.d + 31) / 32) * 32 + 32};
     for (int i = 0; i < 12; ++i) shape[i] = v[i];
   }
+  if (cubin_bytes == nullptr) return PARRM_OK;  // range check only
   return comb_e_compile_only(s, cubin_bytes);
 }
 
