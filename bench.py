@@ -330,6 +330,25 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- B200 arm
+def recorded_pcie_floor(n_gpus: int):
+    """Bare concurrent pinned H2D + D2H of one cfg2 pass per GPU, N ranks at once, as recorded
+    by scripts/pcie_rate.py on an earlier box (profiles/r2/pcie_floor.jsonl) -- context for the
+    e2e figure, not measured in this run."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2", "pcie_floor.jsonl")) as fh:
+            for line in fh:
+                if line.startswith("{"):
+                    rec = json.loads(line)
+                    if rec.get("n_gpus") == n_gpus:
+                        return {"ms_per_step": rec["h2d_d2h_concurrent"]["ms"],
+                                "value": rec["e2e_floor_channel_samples_per_s"],
+                                "source": "profiles/r2/pcie_floor.jsonl (scripts/pcie_rate.py under "
+                                          "torchrun, recorded earlier on another box of this pool)"}
+    except Exception:
+        pass
+    return None
+
+
 def timed_api_passes(dist, fn, steps):
     import torch
 
@@ -509,6 +528,7 @@ def run_b200(args):
             "steps": e2e_steps, "ms_per_step": 1e3 * e2e_seconds / e2e_steps,
             "windows_ms_per_step": [round(1e3 * w / e2e_steps, 3) for w in e2e_windows],
             "slowest_window_pass_ms": e2e_passes[int(np.argmax(e2e_windows))],
+            "pcie_floor": recorded_pcie_floor(world),
             "api": ("PARRM.filter_data() under enable_sharding(gather='none'); this rank's rows "
                     "page-locked in place with pin_array()" if world > 1 else
                     "PARRM.filter_data() on a pinned NumPy array, NumPy result"),
