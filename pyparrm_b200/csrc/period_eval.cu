@@ -17,10 +17,9 @@
 // Kernel 1 (accumulate) walks the samples: one accurate sincos(a_i) per sample, harmonics by
 // the angle-addition recurrence in registers, harmonic sums in registers, and B from
 // shared-memory tiles -- on the FP64 tensor cores (eval_accumulate_tensor_kernel, the default),
-// by scalar FMAs for one or two channels (eval_accumulate_narrow_kernel), or by a register-tiled
-// scalar-FMA GEMM (eval_accumulate_kernel, the first version, kept as an A/B baseline behind
-// PARRM_EVAL_TWO_PHASE=1).  Samples can be split over several CTAs per candidate (few
-// candidates, e.g. Nelder-Mead steps); partials are combined in a fixed order.
+// or by scalar FMAs for one or two channels (eval_accumulate_narrow_kernel).  Samples can be
+// split over several CTAs per candidate (few candidates, e.g. Nelder-Mead steps); partials are
+// combined in a fixed order.
 // Kernel 2 (solve) assembles the Gram matrix, factorises it with partial pivoting (zero pivot
 // -> +inf, the reference's LinAlgError path), solves all channels and reduces the objective.
 
@@ -736,12 +735,11 @@ __device__ unsigned long long g_solve_timing[8];
 #endif
 
 constexpr int kSolveChans = 64;     // channels per pass: one per thread in the substitutions
-constexpr int kSolveThreads = 256;  // ncu on the 64-thread version: ~45k instructions per warp at
-                                    // ~8 cycles each with 6 warps per SM (three CTAs fit by shared
-                                    // memory) -- latency-bound, so the factorisation, the loads
-                                    // and the quadratic form are spread over four times the warps
-constexpr int kGStride = kMaxRows + 2;  // row stride of the Gram matrix: odd, so that the pivot
-                                        // search down a column is free of bank conflicts
+constexpr int kSolveThreads = 256;  // eight warps: rows over warps in the factorisation, four
+                                    // row roles per channel in the substitutions.  80 registers
+                                    // and 74 KB of shared memory: three CTAs per SM
+constexpr int kGStride = kMaxRows + 2;  // row stride of the Gram matrix (odd: walking down a
+                                        // column touches every bank once)
 
 __global__ void __launch_bounds__(kSolveThreads, 3)
 eval_solve_kernel(const double* __restrict__ ws, const double* __restrict__ sumsq, double lambda,
